@@ -1,0 +1,1584 @@
+// dfd_engine.cu -- B200 (sm_100a) window engine for the CODES dragonfly-dally hot path.
+//
+// One persistent cooperative kernel executes the whole simulation.  Simulated time advances in
+// conservative windows [T, T+L): L is the smallest cross-LP delay (a credit delay by default), T the
+// global minimum pending timestamp.  Inside a window every LP that has something due processes its own
+// events strictly in (timestamp, sender gid, sender sequence) order -- one thread per LP, 32 LPs per
+// warp -- and appends the events it emits to the destination LP's inbox.  One grid barrier closes the
+// window; the next T is an atomicMin reduction folded into the same barrier.
+//
+// LP classes:
+//   node   = svr ("nw-lp", model-net-synthetic-dragonfly-all.c) + model-net base LP (model-net-lp.c)
+//            + dragonfly-dally terminal (dragonfly-dally.cxx) of one compute node, fused because they
+//            only exchange zero / sub-ns delay events with each other;
+//   router = dragonfly-dally router LP.
+// The handlers restate the reference's forward handlers; each cites the lines it follows
+// (paths relative to the reference tree, "dally" = src/networks/model-net/dragonfly-dally.cxx,
+// "synthetic" = src/network-workloads/model-net-synthetic-dragonfly-all.c).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (timestamps must be plain IEEE double
+// operations in the reference's order, so FMA contraction is disabled for the whole file).
+
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "dfd_engine.h"
+
+namespace cg = cooperative_groups;
+
+#define INF_BITS 0x7FF0000000000000ULL
+#define NIL 0xFFFFFFFFu
+#define DFD_BLOCK 256
+
+__device__ __forceinline__ double bits2d(unsigned long long b) { return __longlong_as_double((long long)b); }
+__device__ __forceinline__ unsigned long long d2bits(double d) { return (unsigned long long)__double_as_longlong(d); }
+#define DINF bits2d(INF_BITS)
+
+struct Ctx {
+    const DfdParams* P;
+    const DfdArrays* A;
+    double t_end;
+    double cand;  // min timestamp of everything this thread left pending or pushed this window
+    int cur, nxt;
+    unsigned long long ev[EV_NTYPES];
+};
+
+__device__ __forceinline__ void set_error(const DfdArrays& A, unsigned code, unsigned long long info) {
+    if (atomicCAS(&A.counters[2], 0ULL, (unsigned long long)code) == 0ULL) A.counters[3] = info;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CLCG4 (L'Ecuyer-Andres), int32 Schrage form; identical values to ROSS' rng_gen_val
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double clcg4_unif(int32_t* s) {
+    int k, v;
+    double u = 0.0;
+    v = s[0];
+    k = v / 46693;
+    v = 45991 * (v - k * 46693) - k * 25884;
+    if (v < 0) v = v + 2147483647;
+    s[0] = v;
+    u = u + 4.65661287524579692e-10 * v;
+    v = s[1];
+    k = v / 10339;
+    v = 207707 * (v - k * 10339) - k * 870;
+    if (v < 0) v = v + 2147483543;
+    s[1] = v;
+    u = u - 4.65661310075985993e-10 * v;
+    if (u < 0) u = u + 1.0;
+    v = s[2];
+    k = v / 15499;
+    v = 138556 * (v - k * 15499) - k * 3979;
+    if (v < 0) v = v + 2147483423;
+    s[2] = v;
+    u = u + 4.65661336096842131e-10 * v;
+    if (u >= 1.0) u = u - 1.0;
+    v = s[3];
+    k = v / 43218;
+    v = 49689 * (v - k * 43218) - k * 24121;
+    if (v < 0) v = v + 2147483323;
+    s[3] = v;
+    u = u - 4.65661357780891134e-10 * v;
+    if (u < 0) u = u + 1.0;
+    return u;
+}
+// tw_rand_integer: low + (long)(unif * (high + 1 - low)); no draw when high < low
+__device__ __forceinline__ long long clcg4_integer(int32_t* s, long long low, long long high, unsigned long long* draws) {
+    if (high < low) return 0;
+    (*draws)++;
+    return low + (long long)(clcg4_unif(s) * (double)(high + 1 - low));
+}
+
+__device__ __forceinline__ double bytes_to_ns(unsigned long long bytes, double GB_p_s) {  // dally:1588-1599
+    double time = ((double)bytes) / (1024.0 * 1024.0 * 1024.0);
+    time = time / GB_p_s;
+    time = time * 1000.0 * 1000.0 * 1000.0;
+    return time;
+}
+__device__ __forceinline__ double maxd(double a, double b) { return a < b ? b : a; }
+
+// gid arithmetic (codes_mapping.c:149-378 collapsed to closed forms)
+__device__ __forceinline__ unsigned svr_gid(const DfdParams& P, unsigned k) { return (k / P.p) * P.lps_per_rep + P.off_svr + k % P.p; }
+__device__ __forceinline__ unsigned term_gid(const DfdParams& P, unsigned k) { return (k / P.p) * P.lps_per_rep + P.off_term + k % P.p; }
+__device__ __forceinline__ unsigned rtr_gid(const DfdParams& P, unsigned r) { return r * P.lps_per_rep + P.off_rtr; }
+
+__device__ __forceinline__ bool key_less(double ts, unsigned src, unsigned seq, double ts2, unsigned src2, unsigned seq2) {
+    if (ts != ts2) return ts < ts2;
+    if (src != src2) return src < src2;
+    return seq < seq2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// event delivery
+// ------------------------------------------------------------------------------------------------
+// chunk towards a router: append to the router's inbox of the NEXT window parity (drained by the
+// router at the start of the next window, so a record is never read in the window it is written in)
+__device__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (rec.ts >= P.ts_end) return;
+    unsigned idx = atomicAdd(&A.rcin_tail[(size_t)c.nxt * P.NR + r], 1u);
+    if (idx >= (unsigned)P.rcin_cap) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
+        return;
+    }
+    int4* dst = (int4*)&A.rcin[((size_t)c.nxt * P.NR + r) * P.rcin_cap + idx];
+    const int4* src = (const int4*)&rec;
+#pragma unroll
+    for (int i = 0; i < 6; i++) __stcg(dst + i, src[i]);
+    c.cand = fmin(c.cand, rec.ts);
+}
+__device__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (ts >= P.ts_end) return;
+    unsigned idx = atomicAdd(&A.rkin_tail[(size_t)c.nxt * P.NR + r], 1u);
+    if (idx >= (unsigned)P.rkin_cap) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
+        return;
+    }
+    CreditRec rec;
+    rec.ts = ts;
+    rec.src = src;
+    rec.seq = seq;
+    rec.port = (uint16_t)port;
+    rec.vc = (uint8_t)vc;
+    rec.pad0 = 0;
+    rec.pad1 = 0;
+    rec.pad2 = 0;
+    int4* dst = (int4*)&A.rkin[((size_t)c.nxt * P.NR + r) * P.rkin_cap + idx];
+    __stcg(dst, ((const int4*)&rec)[0]);
+    __stcg(dst + 1, ((const int4*)&rec)[1]);
+    c.cand = fmin(c.cand, ts);
+}
+// chunk / credit towards a terminal: single-producer rings (the only sender is the router the terminal
+// hangs off); an empty slot holds ts = +inf, the consumer restores that when it pops.
+__device__ void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (rec.ts >= P.ts_end) return;
+    unsigned idx = A.ncin_tail[n]++;
+    ChunkRec* slot = &A.ncin[(size_t)n * P.ncin_cap + (idx & (P.ncin_cap - 1))];
+    if (d2bits(__ldcg(&slot->ts)) != INF_BITS) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, 0x80000000u | n);
+        return;
+    }
+    int4* dst = (int4*)slot;
+    const int4* src = (const int4*)&rec;
+#pragma unroll
+    for (int i = 5; i >= 0; i--) __stcg(dst + i, src[i]);
+    atomicMin(&A.wake_in[(size_t)c.nxt * P.NT + n], d2bits(rec.ts));
+    c.cand = fmin(c.cand, rec.ts);
+}
+__device__ void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src, unsigned seq) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (ts >= P.ts_end) return;
+    unsigned idx = A.nkin_tail[n]++;
+    CreditRec* slot = &A.nkin[(size_t)n * P.nkin_cap + (idx & (P.nkin_cap - 1))];
+    if (d2bits(__ldcg(&slot->ts)) != INF_BITS) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, 0xC0000000u | n);
+        return;
+    }
+    CreditRec rec;
+    rec.ts = ts;
+    rec.src = src;
+    rec.seq = seq;
+    rec.port = 0;
+    rec.vc = 0;
+    rec.pad0 = 0;
+    rec.pad1 = 0;
+    rec.pad2 = 0;
+    __stcg((int4*)slot + 1, ((const int4*)&rec)[1]);
+    __stcg((int4*)slot, ((const int4*)&rec)[0]);
+    atomicMin(&A.wake_in[(size_t)c.nxt * P.NT + n], d2bits(ts));
+    c.cand = fmin(c.cand, ts);
+}
+
+// ================================================================================================
+// node LP
+// ================================================================================================
+__device__ __forceinline__ void node_add_event(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double ts, unsigned src, unsigned seq,
+                                               unsigned type, unsigned a = 0, unsigned b = 0, unsigned cc = 0, double d = 0.0, unsigned e = 0) {
+    if (ts >= c.P->ts_end) return;
+    if (s->nev >= (unsigned)c.P->nev_cap) {
+        set_error(*c.A, DFD_ERR_NEV_OVERFLOW, n);
+        return;
+    }
+    NodeEv* ev = &list[s->nev++];
+    ev->ts = ts;
+    ev->src = src;
+    ev->seq = seq;
+    ev->type = type;
+    ev->a = a;
+    ev->b = b;
+    ev->c = cc;
+    ev->d = d;
+    ev->e = e;
+    if (s->nev > s->nev_hwm) s->nev_hwm = s->nev;
+}
+
+__device__ __forceinline__ double node_cll(const DfdParams& P, NodeState* s, int32_t* rng) {  // codes/codes.h:61-66
+    s->rng_draws++;
+    return P.lookahead + 0.5 + clcg4_unif(rng) * 0.5;
+}
+
+// issue_event synthetic:231-271: next KICKOFF at now + mean_interval
+__device__ __forceinline__ void svr_issue_event(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
+    const DfdParams& P = *c.P;
+    node_add_event(c, n, s, list, now + P.mean_interval, svr_gid(P, n), s->svr_seq++, EV_KICKOFF);
+}
+
+// handle_kickoff_event synthetic:329-413 + model_net_event_impl_base model-net.c:288-380
+__device__ void svr_kickoff(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
+    const DfdParams& P = *c.P;
+    if (s->msg_sent_count >= P.num_msgs) return;
+    long long local_dest = -1;
+    if (P.traffic == DFD_TR_UNIFORM) {
+        local_dest = clcg4_integer(s->rng_svr0, 1, (long long)P.num_nodes - 2, &s->rng_draws);
+        local_dest = ((long long)n + local_dest) % P.num_nodes;
+    } else if (P.traffic == DFD_TR_NEAREST_GROUP) {
+        local_dest = ((long long)n + P.nodes_per_grp) % P.num_nodes;
+    } else if (P.traffic == DFD_TR_NEAREST_NEIGHBOR) {
+        local_dest = ((long long)n + 1) % P.num_nodes;
+    } else if (P.traffic == DFD_TR_RAND_PERM) {
+        if (s->dest_id == -1 || s->rperm_data > P.rperm_threshold) {
+            s->dest_id = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.num_nodes - 1, &s->rng_draws);
+            local_dest = s->dest_id;
+            s->rperm_data = P.payload_sz;
+        } else {
+            local_dest = s->dest_id;
+            s->rperm_data += P.payload_sz;
+        }
+    } else {  // RANDOM_OTHER_GROUP synthetic:375-392
+        int my_group_id = n / P.nodes_per_grp;
+        int sel = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.G - 2, &s->rng_draws);
+        int rand_group = sel >= my_group_id ? sel + 1 : sel;
+        int rand_node = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.nodes_per_grp - 1, &s->rng_draws);
+        local_dest = (long long)rand_group * P.nodes_per_grp + rand_node;
+    }
+    if (now >= P.warm_up_time) s->warm_msg_sent_count++;
+    s->msg_sent_count++;
+    s->last_send_ts = now;
+    unsigned my_svr = svr_gid(P, n);
+    // model_net_event(net_id, "test", global_dest, PAYLOAD_SZ, 0.0, remote, local, lp)
+    if ((unsigned)local_dest == n && P.payload_sz < P.node_eager_limit && !P.noop_bypass) {
+        // model_net_noop_event model-net.c:252-286 (same terminal on both ends)
+        double poffset = 0.0;
+        double delay = node_cll(P, s, s->rng_svr2);
+        double sendTime = (double)(unsigned long long)P.payload_sz * P.codes_cn_delay;
+        poffset += delay;
+        node_add_event(c, n, s, list, now + (poffset + 0.0 + sendTime), my_svr, s->svr_seq++, EV_LOCAL);
+        poffset += delay;
+        node_add_event(c, n, s, list, now + (poffset + 0.0 + sendTime), my_svr, s->svr_seq++, EV_REMOTE, n, 0, 0, now);
+    } else {
+        double poffset = node_cll(P, s, s->rng_svr2);
+        node_add_event(c, n, s, list, now + (poffset + 0.0), my_svr, s->svr_seq++, EV_NEW_MSG | NEV_FLAG_QREQ, (unsigned)local_dest,
+                       (unsigned)P.payload_sz, 0, now);
+    }
+    svr_issue_event(c, n, s, list, now);
+}
+
+// handle_remote_event synthetic:468-498; the ACK (handle_ack_event :415-432) only updates commutative
+// statistics of the source svr, so it is applied with atomics instead of travelling as an event.
+__device__ void svr_remote(Ctx& c, unsigned n, NodeState* s, double now, unsigned src_svr, double msg_start_time) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (now >= P.warm_up_time) {
+        s->msg_recvd_count++;
+        double packet_latency = now - msg_start_time;
+        s->sum_server_latency += packet_latency;
+        if (packet_latency > s->max_server_latency) s->max_server_latency = packet_latency;
+        s->svr_seq++;  // tw_event_new for the ACK
+        if (now < P.ts_end) {
+            atomicAdd(&A.ack_count[src_svr], 1u);
+            atomicMin(&A.ack_first[src_svr], d2bits(now));
+            atomicMax(&A.ack_last[src_svr], d2bits(now));
+            c.ev[EV_ACK]++;
+        }
+    }
+}
+
+// dragonfly_dally_packet_event dally:5122-5183 via fcfs_next model-net-sched-impl.c:187-261
+__device__ int mn_fcfs_next(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (s->sq_count == 0) return -1;
+    SchedReq* q = &A.sq[(size_t)n * P.nsq_cap + (s->sq_head & (P.nsq_cap - 1))];
+    int is_last_packet;
+    unsigned psize;
+    if (P.mn_packet_size >= q->rem) {
+        psize = q->rem;
+        is_last_packet = 1;
+    } else {
+        psize = P.mn_packet_size;
+        is_last_packet = 0;
+    }
+    node_add_event(c, n, s, list, now + 0.0, term_gid(P, n), s->term_seq++, EV_T_GENERATE | (is_last_packet ? NEV_FLAG_LAST : 0), q->dst_svr,
+                   q->msg_size, psize, q->msg_start_time, q->msg_id);
+    if (is_last_packet) {
+        s->sq_head++;
+        s->sq_count--;
+        return 1;
+    }
+    q->rem -= psize;
+    return 0;
+}
+__device__ __forceinline__ void mn_sched_next(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {  // model-net-lp.c:838-873
+    if (mn_fcfs_next(c, n, s, list, now) == -1) s->in_sched_send_loop = 0;
+}
+
+// handle_new_msg model-net-lp.c:643-802
+__device__ void mn_new_msg(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const NodeEv& ev) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (ev.a == n) {  // lp->gid == dest_mn_lp: self-addressed message above the eager limit
+        set_error(A, DFD_ERR_SELF_SEND, n);
+        return;
+    }
+    if (ev.type & NEV_FLAG_QREQ) {
+        double exp_time = (s->next_available_time > now) ? s->next_available_time : now;
+        exp_time += P.nic_seq_delay + node_cll(P, s, s->rng_term2);
+        s->next_available_time = exp_time;
+        node_add_event(c, n, s, list, now + (exp_time - now), term_gid(P, n), s->term_seq++, EV_NEW_MSG, ev.a, ev.b, 0, ev.d);
+        return;
+    }
+    if (s->sq_count >= (unsigned)P.nsq_cap) {
+        set_error(A, DFD_ERR_SQ_OVERFLOW, n);
+        return;
+    }
+    SchedReq* q = &A.sq[(size_t)n * P.nsq_cap + ((s->sq_head + s->sq_count) & (P.nsq_cap - 1))];
+    q->dst_svr = ev.a;
+    q->msg_size = ev.b;
+    q->rem = ev.b;
+    q->msg_id = s->msg_id++;
+    q->msg_start_time = ev.d;
+    s->sq_count++;
+    if (s->sq_count > s->sq_hwm) s->sq_hwm = s->sq_count;
+    if (s->in_sched_send_loop == 0) {
+        s->in_sched_send_loop = 1;
+        mn_sched_next(c, n, s, list, now);
+    }
+}
+
+__device__ __forceinline__ unsigned num_chunks_for(unsigned sz, unsigned chunk) { return sz ? (sz + chunk - 1) / chunk : 1; }  // dally:103-104
+
+// packet_generate dally:5417-5774
+__device__ void term_packet_generate(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const NodeEv& ev) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    unsigned dst_svr = ev.a, total_size = ev.b, packet_size = ev.c, message_id = ev.e;
+    unsigned dst_term = dst_svr;  // one svr per terminal
+    s->packet_gen++;
+    s->total_gen_size += packet_size;
+    unsigned nchunks = num_chunks_for(packet_size, P.chunk_size);
+    int my_router = n / P.p;
+    int dest_router_id = dst_term / P.p;
+    int dest_grp_id = dest_router_id / P.a;
+    int src_grp_id = my_router / P.a;
+    if (src_grp_id == dest_grp_id) {
+        if (dest_router_id == my_router)
+            s->local_sr++;
+        else
+            s->local_sg++;
+    } else
+        s->remote_pk++;
+    unsigned packet_id = s->packet_counter++;
+    unsigned flags = (ev.type & NEV_FLAG_LAST) ? 3u : 0u;  // remote + local event ride on the last packet
+    for (unsigned i = 0; i < nchunks; i++) {
+        if (s->tq_count >= (unsigned)P.ntq_cap) {
+            set_error(A, DFD_ERR_TQ_OVERFLOW, n);
+            return;
+        }
+        TermChunk* t = &A.tq[(size_t)n * P.ntq_cap + ((s->tq_head + s->tq_count) & (P.ntq_cap - 1))];
+        t->dst_svr = dst_svr;
+        t->packet_id = packet_id;
+        t->packet_size = packet_size;
+        t->total_size = total_size;
+        t->message_id = message_id;
+        t->chunk_id = i;
+        t->flags = flags;
+        t->msg_start_time = ev.d;
+        s->tq_count++;
+        s->terminal_length += P.chunk_size;
+    }
+    if (s->tq_count > s->tq_hwm) s->tq_hwm = s->tq_count;
+    double injection_ts = bytes_to_ns(packet_size, P.cn_bw);
+    double nic_ts = injection_ts;
+    unsigned tg = term_gid(P, n);
+    if (s->terminal_length < P.cn_vc) {
+        node_add_event(c, n, s, list, now + nic_ts, tg, s->term_seq++, EV_SCHED_NEXT);  // model_net_method_idle_event2
+    } else {
+        s->issueIdle = 1;
+        if (s->last_buf_full == 0.0) s->last_buf_full = now;
+    }
+    if (s->in_send_loop == 0) {
+        node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_T_SEND);
+        s->in_send_loop = 1;
+    }
+    long long total_event_size = 416 + ((flags & 1) ? 72 : 0) + ((flags & 2) ? 72 : 0);  // model-net.c:500-504, sizeof(svr_msg)=72
+    s->stats_used = 1;
+    s->send_count++;
+    s->send_bytes += packet_size;
+    s->send_time += (1 / P.cn_bw) * packet_size;
+    if (s->max_event_size < total_event_size) s->max_event_size = total_event_size;
+}
+
+// packet_send dally:5836-6026 (+ get_next_vcg :3440-3449 for one QoS level)
+__device__ void term_packet_send(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (s->tq_count == 0 || s->vc_occupancy + P.chunk_size > P.cn_vc) {
+        s->in_send_loop = 0;
+        s->stalled_chunks++;
+        if (!s->last_buf_full) s->last_buf_full = now;
+        return;
+    }
+    TermChunk cur = A.tq[(size_t)n * P.ntq_cap + (s->tq_head & (P.ntq_cap - 1))];
+    unsigned nchunks = num_chunks_for(cur.packet_size, P.chunk_size);
+    double injection_delay = bytes_to_ns(P.chunk_size, P.cn_bw);
+    if ((cur.packet_size < (unsigned)P.chunk_size) && (cur.chunk_id == nchunks - 1)) {
+        unsigned data_size = cur.packet_size % P.chunk_size;
+        injection_delay = bytes_to_ns(data_size, P.cn_bw);
+    }
+    double propagation_delay = P.cn_delay;
+    s->terminal_available_time = maxd(s->terminal_available_time, now);
+    s->terminal_available_time += injection_delay;
+    double injection_ts = s->terminal_available_time - now;
+    double propagation_ts = injection_ts + propagation_delay;
+    unsigned tg = term_gid(P, n);
+    {
+        ChunkRec rec;
+        rec.ts = now + propagation_ts;
+        rec.src = tg;
+        rec.seq = s->term_seq++;
+        rec.packet_id = cur.packet_id;
+        rec.src_term = n;
+        rec.dst_term = cur.dst_svr;
+        rec.message_id = cur.message_id;
+        rec.packet_size = cur.packet_size;
+        rec.total_size = cur.total_size;
+        rec.chunk_id = cur.chunk_id;
+        rec.intm_grp_id = -1;
+        rec.prev_lp = n;
+        rec.prev_port = 0;  // vc_index = vcg = 0
+        rec.prev_vc = 0;    // output_chan = vcg
+        rec.last_hop = DFD_HOP_TERMINAL;
+        rec.path_type = -1;
+        rec.is_intm_visited = 0;
+        rec.n_hop = rec.l_hop = rec.g_hop = rec.hops_cur_group = 0;
+        rec.flags = (uint8_t)(cur.flags & 1u);  // local_event_size_bytes = 0 on the wire
+        rec.pad0 = 0;
+        rec.travel_start_time = now;
+        rec.msg_start_time = cur.msg_start_time;
+        rec.origin_router = n / P.p;
+        rec.src_svr = n;
+        rec.dst_svr = cur.dst_svr;
+        rec.pad1 = 0;
+        push_chunk_to_router(c, n / P.p, rec);
+    }
+    if (cur.chunk_id == nchunks - 1 && (cur.flags & 2u)) {  // LOCAL completion event to the sender svr at +0
+        node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_LOCAL);
+    }
+    s->vc_occupancy += P.chunk_size;
+    s->tq_head++;
+    s->tq_count--;
+    s->terminal_length -= P.chunk_size;
+    s->link_traffic += P.chunk_size;
+    s->total_chunks++;
+    s->injected_chunks++;
+    if (s->tq_count != 0 && s->vc_occupancy + P.chunk_size <= P.cn_vc) {
+        node_add_event(c, n, s, list, now + injection_ts, tg, s->term_seq++, EV_T_SEND);
+    } else {
+        s->in_send_loop = 0;
+    }
+    if (s->issueIdle && s->terminal_length < P.cn_vc) {
+        s->issueIdle = 0;
+        node_add_event(c, n, s, list, now + injection_ts, tg, s->term_seq++, EV_SCHED_NEXT);
+        if (s->last_buf_full > 0.0) {
+            s->busy_time += (now - s->last_buf_full);
+            s->last_buf_full = 0.0;
+        }
+    }
+}
+
+// terminal_buf_update dally:6762-6789
+__device__ __forceinline__ void term_buf_update(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
+    const DfdParams& P = *c.P;
+    s->vc_occupancy -= P.chunk_size;
+    if (s->in_send_loop == 0 && s->tq_count != 0) {
+        node_add_event(c, n, s, list, now + 0.0, term_gid(P, n), s->term_seq++, EV_T_SEND);
+        s->in_send_loop = 1;
+    }
+}
+
+// packet_arrive dally:6453-6744 (single-chunk packets, single-packet messages: the reassembly entry is
+// created and retired inside this one call)
+__device__ void term_packet_arrive(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const ChunkRec& m) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    if (m.dst_term != n) {
+        set_error(A, DFD_ERR_WRONG_TERMINAL, n);
+        return;
+    }
+    unsigned tg = term_gid(P, n);
+    push_credit_to_router(c, m.prev_lp, now + P.cn_credit, tg, s->term_seq++, m.prev_port, m.prev_vc);
+    s->finished_chunks++;
+    s->ejected_chunks++;
+    if (m.path_type == DFD_MINIMAL) s->minimal_count++;
+    if (m.path_type == DFD_NON_MINIMAL) s->nonmin_count++;
+    double ete_latency = now - m.travel_start_time;
+    s->total_time += ete_latency;
+    s->total_hops += m.n_hop;
+    s->stats_used = 1;
+    s->recv_time += ete_latency;
+    unsigned nchunks = num_chunks_for(m.packet_size, P.chunk_size);
+    if (m.chunk_id == nchunks - 1) {
+        s->packet_fin++;
+        s->recv_count++;
+        s->recv_bytes += m.packet_size;
+        s->finished_packets++;
+    }
+    if (s->min_latency > ete_latency) s->min_latency = ete_latency;
+    if (s->max_latency < ete_latency) s->max_latency = ete_latency;
+    // packet complete (chunk_size >= packet_size) and message complete (one packet)
+    s->total_msg_size += m.total_size;
+    s->finished_msgs++;
+    if (m.flags & 1u)  // send_remote_event dally:6124-6151: REMOTE to the destination svr at +0
+        node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_REMOTE, m.src_svr, 0, 0, m.msg_start_time);
+}
+
+__device__ void node_process(Ctx& c, unsigned n) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    NodeState* s = &A.node[n];
+    NodeEv* list = &A.nev[(size_t)n * P.nev_cap];
+    const unsigned cmask = P.ncin_cap - 1, kmask = P.nkin_cap - 1;
+    double next_ts;
+    for (;;) {
+        // earliest self event
+        int bi = -1;
+        double bts = DINF;
+        unsigned bsrc = 0, bseq = 0;
+        int kind = 0;  // 0 self, 1 chunk ring, 2 credit ring
+        for (unsigned i = 0; i < s->nev; i++) {
+            const NodeEv& e = list[i];
+            if (bi < 0 || key_less(e.ts, e.src, e.seq, bts, bsrc, bseq)) {
+                bi = (int)i;
+                bts = e.ts;
+                bsrc = e.src;
+                bseq = e.seq;
+            }
+        }
+        ChunkRec* ch = &A.ncin[(size_t)n * P.ncin_cap + (s->cin_head & cmask)];
+        int4 chh = __ldcg((const int4*)ch);
+        double cts = __longlong_as_double(((long long)(unsigned)chh.y << 32) | (unsigned)chh.x);
+        if (d2bits(cts) != INF_BITS && (bts == DINF || key_less(cts, (unsigned)chh.z, (unsigned)chh.w, bts, bsrc, bseq))) {
+            kind = 1;
+            bts = cts;
+            bsrc = (unsigned)chh.z;
+            bseq = (unsigned)chh.w;
+        }
+        CreditRec* kr = &A.nkin[(size_t)n * P.nkin_cap + (s->kin_head & kmask)];
+        int4 krh = __ldcg((const int4*)kr);
+        double kts = __longlong_as_double(((long long)(unsigned)krh.y << 32) | (unsigned)krh.x);
+        if (d2bits(kts) != INF_BITS && (bts == DINF || key_less(kts, (unsigned)krh.z, (unsigned)krh.w, bts, bsrc, bseq))) {
+            kind = 2;
+            bts = kts;
+            bsrc = (unsigned)krh.z;
+            bseq = (unsigned)krh.w;
+        }
+        if (!(bts < c.t_end)) {
+            next_ts = bts;
+            break;
+        }
+        double now = bts;
+        s->events++;
+        if (kind == 1) {
+            ChunkRec m;
+            int4* dst = (int4*)&m;
+            dst[0] = chh;
+#pragma unroll
+            for (int i = 1; i < 6; i++) dst[i] = __ldcg((const int4*)ch + i);
+            __stcg((unsigned long long*)&ch->ts, INF_BITS);
+            s->cin_head++;
+            c.ev[EV_T_ARRIVE]++;
+            term_packet_arrive(c, n, s, list, now, m);
+        } else if (kind == 2) {
+            __stcg((unsigned long long*)&kr->ts, INF_BITS);
+            s->kin_head++;
+            c.ev[EV_T_BUFFER]++;
+            term_buf_update(c, n, s, list, now);
+        } else {
+            NodeEv ev = list[bi];
+            list[bi] = list[s->nev - 1];
+            s->nev--;
+            unsigned type = ev.type & 0xFF;
+            c.ev[type]++;
+            switch (type) {
+            case EV_KICKOFF: svr_kickoff(c, n, s, list, now); break;
+            case EV_REMOTE: svr_remote(c, n, s, now, ev.a, ev.d); break;
+            case EV_LOCAL:  // handle_local_event synthetic:508-516
+                if (now >= P.warm_up_time) s->local_recvd_count++;
+                break;
+            case EV_NEW_MSG: mn_new_msg(c, n, s, list, now, ev); break;
+            case EV_SCHED_NEXT: mn_sched_next(c, n, s, list, now); break;
+            case EV_T_GENERATE: term_packet_generate(c, n, s, list, now, ev); break;
+            case EV_T_SEND: term_packet_send(c, n, s, list, now); break;
+            default: break;
+            }
+        }
+    }
+    A.wake_self[n] = d2bits(next_ts);
+    c.cand = fmin(c.cand, next_ts);
+}
+
+// ================================================================================================
+// router LP
+// ================================================================================================
+struct RCtx {
+    unsigned r;       // router id
+    unsigned gid;
+    int lid, grp;
+    RouterHdr* h;
+    PortState* port;
+    PortQ* pq;
+    PoolSlot* pool;
+    RHeapEnt* heap;
+};
+
+__device__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
+    if (ts >= c.P->ts_end) return;
+    unsigned n = R.h->heap_n;
+    if (n >= (unsigned)c.P->rheap_cap) {
+        set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
+        return;
+    }
+    RHeapEnt* H = R.heap;
+    unsigned i = n;
+    while (i > 0) {
+        unsigned p = (i - 1) >> 1;
+        RHeapEnt pe = H[p];
+        if (!key_less(ts, src, seq, pe.ts, pe.src, pe.seq)) break;
+        H[i] = pe;
+        i = p;
+    }
+    H[i].ts = ts;
+    H[i].src = src;
+    H[i].seq = seq;
+    H[i].ref = ref;
+    R.h->heap_n = n + 1;
+    if (n + 1 > R.h->heap_hwm) R.h->heap_hwm = n + 1;
+}
+__device__ RHeapEnt rheap_pop(RCtx& R) {
+    RHeapEnt* H = R.heap;
+    RHeapEnt top = H[0];
+    unsigned n = --R.h->heap_n;
+    if (n > 0) {
+        RHeapEnt last = H[n];
+        unsigned i = 0;
+        for (;;) {
+            unsigned l = 2 * i + 1;
+            if (l >= n) break;
+            unsigned rr = l + 1;
+            unsigned m = l;
+            RHeapEnt me = H[l];
+            if (rr < n) {
+                RHeapEnt re = H[rr];
+                if (key_less(re.ts, re.src, re.seq, me.ts, me.src, me.seq)) {
+                    m = rr;
+                    me = re;
+                }
+            }
+            if (!key_less(me.ts, me.src, me.seq, last.ts, last.src, last.seq)) break;
+            H[i] = me;
+            i = m;
+        }
+        H[i] = last;
+    }
+    return top;
+}
+
+// --- connection queries (DragonflyConnectionManager, dragonfly-network-manager.cxx) ----------------
+// local ports from my local id to router-local id `lid` (get_connections_to_gid(.., CONN_LOCAL)): file order
+__device__ __forceinline__ void loc_range(const DfdParams& P, const DfdArrays& A, int mylid, int lid, int* lo, int* hi) {
+    *lo = A.loc_off[mylid * P.a + lid];
+    *hi = A.loc_off[mylid * P.a + lid + 1];
+}
+// direct global connections to group g (get_connections_to_group): contiguous range of the by-dest-gid list
+__device__ __forceinline__ void grp_range(const DfdParams& P, const DfdArrays& A, unsigned r, int g, int* lo, int* hi) {
+    const int* gg = A.gs_group + (size_t)r * P.h;
+    int l = 0;
+    while (l < P.h && gg[l] < g) l++;
+    int u = l;
+    while (u < P.h && gg[u] == g) u++;
+    *lo = l;
+    *hi = u;
+}
+
+// a candidate list of next-hop connections, never materialised:
+//  kind 0: empty; 1: direct global links [lo,hi) of the by-gid list; 2: "routed" list towards group g
+//  (for each global link my group -> g in inter-file order: all my local links to its owner,
+//  get_routed_connections_to_group(g, true) network-manager.cxx:772-814); 3: local links to lid lo
+struct Cands {
+    int kind, lo, hi, n;
+};
+__device__ int routed_count(const DfdParams& P, const DfdArrays& A, const RCtx& R, int g) {
+    int o0 = A.routed_off[R.grp * P.G + g], o1 = A.routed_off[R.grp * P.G + g + 1];
+    int n = 0;
+    for (int i = o0; i < o1; i++) {
+        int lid = A.routed_lid[i];
+        n += A.loc_off[R.lid * P.a + lid + 1] - A.loc_off[R.lid * P.a + lid];
+    }
+    return n;
+}
+__device__ int cand_port(const DfdParams& P, const DfdArrays& A, const RCtx& R, const Cands& cd, int idx) {
+    if (cd.kind == 1) return A.gs_port[(size_t)R.r * P.h + cd.lo + idx];
+    if (cd.kind == 3) return A.loc_port[cd.lo + idx];
+    // kind 2
+    int o0 = A.routed_off[R.grp * P.G + cd.lo], o1 = A.routed_off[R.grp * P.G + cd.lo + 1];
+    for (int i = o0; i < o1; i++) {
+        int lid = A.routed_lid[i];
+        int l0 = A.loc_off[R.lid * P.a + lid], l1 = A.loc_off[R.lid * P.a + lid + 1];
+        if (idx < l1 - l0) return A.loc_port[l0 + idx];
+        idx -= l1 - l0;
+    }
+    return -1;
+}
+// get_legal_minimal_stops dally:9793-9849
+__device__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, const RCtx& R, int fdest_router) {
+    Cands cd;
+    int fg = fdest_router / P.a;
+    if (R.grp != fg) {
+        grp_range(P, A, R.r, fg, &cd.lo, &cd.hi);
+        if (cd.hi > cd.lo) {
+            cd.kind = 1;
+            cd.n = cd.hi - cd.lo;
+            return cd;
+        }
+        cd.kind = 2;
+        cd.lo = fg;
+        cd.hi = 0;
+        cd.n = routed_count(P, A, R, fg);
+        return cd;
+    }
+    int lo, hi;
+    loc_range(P, A, R.lid, fdest_router % P.a, &lo, &hi);
+    cd.kind = 3;
+    cd.lo = lo;
+    cd.hi = hi;
+    cd.n = hi - lo;
+    return cd;
+}
+
+__device__ __forceinline__ int score_port(const DfdParams& P, const RCtx& R, int port, bool nonmin) {  // dally:1649-1684
+    if (port < 0) return 2147483647;
+    const PortState& ps = R.port[port];
+    int score = ps.vc_occ[0] + ps.vc_occ[1] + ps.vc_occ[2] + ps.vc_occ[3] + ps.queued_count;
+    if (P.scoring == DFD_SCORE_DELTA && nonmin) score = score * 2;
+    return score;
+}
+__device__ __forceinline__ long long r_integer(RCtx& R, long long lo, long long hi) { return clcg4_integer(R.h->rng, lo, hi, &R.h->rng_draws); }
+
+// get_absolute_best_connection_from_conns dally:1687-1723 over a candidate list
+__device__ int best_from_cands(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
+    if (cd.n == 0) return -1;
+    if (cd.n == 1) return cand_port(P, A, R, cd, 0);
+    int best_score = 2147483647, nbest = 0;
+    for (int i = 0; i < cd.n; i++) {
+        int sc = score_port(P, R, cand_port(P, A, R, cd, i), false);
+        if (sc < best_score) {
+            best_score = sc;
+            nbest = 1;
+        } else if (sc == best_score)
+            nbest++;
+    }
+    int pick = (int)r_integer(R, 0, nbest - 1);
+    for (int i = 0; i < cd.n; i++) {
+        int port = cand_port(P, A, R, cd, i);
+        if (score_port(P, R, port, false) == best_score) {
+            if (pick == 0) return port;
+            pick--;
+        }
+    }
+    return -1;
+}
+// dfdally_get_best_from_k_connections dally:1796-1859 with k == 2
+__device__ int best_from_k2(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
+    if (cd.n == 0) return -1;
+    if (cd.n == 1) return cand_port(P, A, R, cd, 0);
+    long long n = cd.n;
+    long long s1 = r_integer(R, 0, n - 1);
+    long long off = r_integer(R, 1, n - 1);
+    long long s2 = (s1 + off) % n;
+    int p1 = cand_port(P, A, R, cd, (int)s1), p2 = cand_port(P, A, R, cd, (int)s2);
+    int sc1 = score_port(P, R, p1, false), sc2 = score_port(P, R, p2, false);
+    // best of the two polled connections; ties broken by one more draw (always drawn: size == 2)
+    if (sc1 < sc2) {
+        r_integer(R, 0, 0);
+        return p1;
+    }
+    if (sc2 < sc1) {
+        r_integer(R, 0, 0);
+        return p2;
+    }
+    return r_integer(R, 0, 1) == 0 ? p1 : p2;
+}
+
+// dfdally_select_intermediate_group dally:9738-9790
+__device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m, int fdest_router) {
+    int fg = fdest_router / P.a;
+    int og = m.origin_router / P.a;
+    if (m.intm_grp_id == -1) {
+        int sel = (int)r_integer(R, 0, (long long)P.G - 3);  // groups other than origin and destination, ascending
+        int lo = og < fg ? og : fg, hi = og < fg ? fg : og;
+        int g = sel;
+        if (g >= lo) g++;
+        if (g >= hi) g++;
+        m.intm_grp_id = g;
+    } else {
+        // re-pick among the groups this router links to directly (set<int>: ascending, unique)
+        const int* gg = A.gs_group + (size_t)R.r * P.h;
+        int nvalid = 0, prev = -1;
+        for (int i = 0; i < P.h; i++) {
+            int g = gg[i];
+            if (g != prev && g != fg && g != og) nvalid++;
+            prev = g;
+        }
+        int sel = (int)r_integer(R, 0, (long long)nvalid - 1);
+        prev = -1;
+        for (int i = 0; i < P.h; i++) {
+            int g = gg[i];
+            if (g != prev && g != fg && g != og) {
+                if (sel == 0) {
+                    m.intm_grp_id = g;
+                    break;
+                }
+                sel--;
+            }
+            prev = g;
+        }
+    }
+}
+
+// get_legal_nonminimal_stops dally:9853-9910
+__device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m, int fdest_router) {
+    Cands cd;
+    cd.kind = 0;
+    cd.lo = cd.hi = cd.n = 0;
+    int og = m.origin_router / P.a;
+    if (R.grp == og) {
+        grp_range(P, A, R.r, m.intm_grp_id, &cd.lo, &cd.hi);
+        if (cd.hi > cd.lo) {
+            cd.kind = 1;
+            cd.n = cd.hi - cd.lo;
+            return cd;
+        }
+        if (R.r == m.origin_router) {
+            cd.kind = 2;
+            cd.lo = m.intm_grp_id;
+            cd.n = routed_count(P, A, R, m.intm_grp_id);
+            return cd;
+        }
+        select_intermediate_group(P, A, R, m, fdest_router);
+        grp_range(P, A, R.r, m.intm_grp_id, &cd.lo, &cd.hi);
+        cd.kind = 1;
+        cd.n = cd.hi - cd.lo;
+        return cd;
+    }
+    return cd;
+}
+
+// do_dfdally_routing dally:7110-7215 -> output port
+__device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    int fg = fdest_router / P.a;
+    if ((int)R.r == fdest_router) {  // destination router: the terminal port (one rail -> no draw)
+        return P.intra_radix + P.global_radix + (int)(m.dst_term % P.p);
+    } else if (R.grp == fg) {  // destination group: local link(s) to the destination router
+        Cands cd;
+        loc_range(P, A, R.lid, fdest_router % P.a, &cd.lo, &cd.hi);
+        cd.kind = 3;
+        cd.n = cd.hi - cd.lo;
+        if (cd.n < 1) {
+            set_error(A, DFD_ERR_DEAD_END, R.r);
+            return -1;
+        }
+        if (P.routing == DFD_PROG_ADAPTIVE) return best_from_cands(P, A, R, cd);
+        return cand_port(P, A, R, cd, (int)r_integer(R, 0, cd.n - 1));
+    }
+    if (m.last_hop == DFD_HOP_TERMINAL && m.intm_grp_id == -1) select_intermediate_group(P, A, R, m, fdest_router);
+    if (P.routing == DFD_MINIMAL) {  // dfdally_minimal_routing dally:9913-9932
+        Cands cd = legal_minimal_stops(P, A, R, fdest_router);
+        if (cd.n < 1) {
+            set_error(A, DFD_ERR_DEAD_END, R.r);
+            return -1;
+        }
+        return cand_port(P, A, R, cd, (int)r_integer(R, 0, cd.n - 1));
+    }
+    if (P.routing == DFD_NON_MINIMAL) {  // dfdally_nonminimal_routing dally:9939-9992
+        m.path_type = DFD_NON_MINIMAL;
+        if (R.grp == m.intm_grp_id) m.is_intm_visited = 1;
+        int next_group = m.is_intm_visited == 1 ? fg : m.intm_grp_id;
+        Cands cd;
+        grp_range(P, A, R.r, next_group, &cd.lo, &cd.hi);
+        if (cd.hi > cd.lo) {
+            cd.kind = 1;
+            cd.n = cd.hi - cd.lo;
+        } else {
+            cd.kind = 2;
+            cd.lo = next_group;
+            cd.n = routed_count(P, A, R, next_group);
+        }
+        if (cd.n < 1) {
+            set_error(A, DFD_ERR_DEAD_END, R.r);
+            return -1;
+        }
+        return cand_port(P, A, R, cd, (int)r_integer(R, 0, cd.n - 1));
+    }
+    // dfdally_prog_adaptive_routing dally:9995-10061
+    if (R.grp == m.intm_grp_id) m.is_intm_visited = 1;
+    Cands mins = legal_minimal_stops(P, A, R, fdest_router);
+    Cands nonmins = legal_nonminimal_stops(P, A, R, m, fdest_router);
+    int best_min, best_non;
+    if (mins.n > 0 && mins.kind == 1)
+        best_min = best_from_k2(P, A, R, mins);
+    else
+        best_min = best_from_cands(P, A, R, mins);
+    if (nonmins.n > 0 && nonmins.kind == 1)
+        best_non = best_from_k2(P, A, R, nonmins);
+    else
+        best_non = best_from_cands(P, A, R, nonmins);
+    int min_score = score_port(P, R, best_min, false);
+    int non_score = score_port(P, R, best_non, true);
+    if (m.path_type == DFD_NON_MINIMAL && m.is_intm_visited != 1) return best_non;
+    if (min_score <= P.adaptive_threshold) return best_min;
+    if (min_score <= non_score) return best_min;
+    m.path_type = DFD_NON_MINIMAL;
+    return best_non;
+}
+
+// router_credit_send dally:7269-7326
+__device__ void router_credit_send(Ctx& c, RCtx& R, double now, unsigned last_hop, unsigned prev_lp, unsigned port, unsigned vc) {
+    const DfdParams& P = *c.P;
+    unsigned seq = R.h->seq++;
+    if (last_hop == DFD_HOP_TERMINAL)
+        push_credit_to_node(c, prev_lp, now + P.cn_credit, R.gid, seq);
+    else if (last_hop == DFD_HOP_GLOBAL)
+        push_credit_to_router(c, prev_lp, now + P.global_credit, R.gid, seq, port, vc);
+    else
+        push_credit_to_router(c, prev_lp, now + P.local_credit, R.gid, seq, port, vc);
+}
+
+__device__ __forceinline__ void fifo_append(PoolSlot* pool, uint32_t* head, uint32_t* tail, unsigned slot) {
+    pool[slot].next = NIL;
+    if (*tail == NIL)
+        *head = slot;
+    else
+        pool[*tail].next = slot;
+    *tail = slot;
+}
+__device__ __forceinline__ unsigned fifo_pop(PoolSlot* pool, uint32_t* head, uint32_t* tail) {
+    unsigned s = *head;
+    *head = pool[s].next;
+    if (*head == NIL) *tail = NIL;
+    return s;
+}
+
+// router_packet_receive dally:7377-7595; the chunk already sits in pool slot `slot`
+__device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    PoolSlot& m = R.pool[slot];
+    int dest_router_id = m.dst_term / P.p;
+    int in_path_type = m.path_type;  // msg->path_type (as received)
+    unsigned in_port = m.prev_port, in_vc = m.prev_vc, in_last_hop = m.last_hop, in_prev = m.prev_lp;
+    if (m.last_hop == DFD_HOP_TERMINAL) m.path_type = DFD_MINIMAL;
+    int output_port = do_routing(c, R, m, dest_router_id);
+    if (output_port < 0 || output_port >= P.radix) {
+        set_error(A, DFD_ERR_DEAD_END, R.r);
+        return;
+    }
+    int conn_local = output_port < P.intra_radix;
+    int conn_global = !conn_local && output_port < P.intra_radix + P.global_radix;
+    if (conn_local) {
+        int dlid = A.loc_dest[R.lid * P.intra_radix + output_port];
+        m.next_stop = R.grp * P.a + dlid;
+        m.next_is_term = 0;
+    } else if (conn_global) {
+        m.next_stop = A.gdest[(size_t)R.r * P.h + (output_port - P.intra_radix)];
+        m.next_is_term = 0;
+    } else {
+        m.next_stop = m.dst_term;
+        m.next_is_term = 1;
+    }
+    m.out_port = (uint16_t)output_port;
+    int max_vc_size = P.cn_vc;
+    int src_group_id = m.origin_router / P.a;
+    int dest_group_id = dest_router_id / P.a;
+    int output_chan = 0;
+    if (R.grp == src_group_id) {
+        output_chan = m.l_hop;
+        if (in_path_type == DFD_NON_MINIMAL) output_chan = 1;
+    } else if (R.grp != dest_group_id) {
+        output_chan = 2;
+    } else {
+        output_chan = 3;
+    }
+    if (conn_local) {
+        max_vc_size = P.local_vc;
+        m.l_hop++;
+        m.hops_cur_group++;
+    }
+    if (conn_global) {
+        max_vc_size = P.global_vc;
+        m.hops_cur_group = 0;
+        m.g_hop++;
+    }
+    if (output_chan >= DFD_NUM_VCS) {
+        set_error(A, DFD_ERR_BAD_VC, R.r);
+        return;
+    }
+    m.out_vc = (uint8_t)output_chan;
+    m.n_hop++;
+    PortState& ps = R.port[output_port];
+    PortQ& pq = R.pq[output_port];
+    if (ps.vc_occ[output_chan] + P.chunk_size <= max_vc_size) {
+        router_credit_send(c, R, now, in_last_hop, in_prev, in_port, in_vc);
+        fifo_append(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan], slot);
+        ps.vc_occ[output_chan] += P.chunk_size;
+        if (ps.in_send_loop == 0) {
+            double ts = maxd(ps.noat, now) - now;
+            rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
+            ps.in_send_loop = 1;
+        }
+    } else {
+        ps.stalled_chunks++;
+        // saved_vc / saved_channel = upstream port / vc: already kept in prev_port / prev_vc
+        fifo_append(R.pool, &pq.queue_head[output_chan], &pq.queue_tail[output_chan], slot);
+        ps.queued_count += P.chunk_size;
+        if (ps.last_buf_full == 0.0) ps.last_buf_full = now;
+    }
+}
+
+// router_packet_send dally:7705-8032 (+ get_next_router_vcg :3499-3557)
+__device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port) {
+    const DfdParams& P = *c.P;
+    PortState& ps = R.port[output_port];
+    PortQ& pq = R.pq[output_port];
+    int output_chan = -1;
+    {
+        int next_rr_vc = (ps.last_qos_lvl + 1) % DFD_NUM_VCS;
+        for (int i = 0; i < DFD_NUM_VCS; i++) {
+            if (pq.pend_head[next_rr_vc] != NIL) {
+                ps.last_qos_lvl = (uint8_t)next_rr_vc;
+                output_chan = next_rr_vc;
+                break;
+            }
+            next_rr_vc = (next_rr_vc + 1) % DFD_NUM_VCS;
+        }
+    }
+    if (output_chan < 0) {
+        ps.in_send_loop = 0;
+        if (ps.queued_count && !ps.last_buf_full) ps.last_buf_full = now;
+        return;
+    }
+    unsigned slot = pq.pend_head[output_chan];
+    PoolSlot& m = R.pool[slot];
+    if (ps.last_buf_full) {
+        ps.busy_time += (now - ps.last_buf_full);
+        ps.last_buf_full = 0.0;
+    }
+    int to_terminal = 1, global = 0;
+    double delay = P.cn_delay;
+    double bandwidth = P.cn_bw;
+    if (output_port < P.intra_radix) {
+        to_terminal = 0;
+        delay = P.local_delay;
+        bandwidth = P.local_bw;
+    } else if (output_port < P.intra_radix + P.num_global_channels) {
+        to_terminal = 0;
+        global = 1;
+        delay = P.global_delay;
+        bandwidth = P.global_bw;
+    }
+    unsigned nchunks = num_chunks_for(m.packet_size, P.chunk_size);
+    double propagation_delay = delay;
+    double injection_delay = bytes_to_ns(P.chunk_size, bandwidth);
+    if (m.packet_size == 0) injection_delay = bytes_to_ns(P.credit_size, bandwidth);
+    if ((m.packet_size < (unsigned)P.chunk_size) && (m.chunk_id == nchunks - 1))
+        injection_delay = bytes_to_ns(m.packet_size % P.chunk_size, bandwidth);
+    injection_delay += P.router_delay;
+    ps.noat = maxd(ps.noat, now);
+    ps.noat += injection_delay;
+    double injection_ts = ps.noat - now;
+    double propagation_ts = injection_ts + propagation_delay;
+    {
+        ChunkRec rec;
+        rec.ts = now + propagation_ts;
+        rec.src = R.gid;
+        rec.seq = R.h->seq++;
+        rec.packet_id = m.packet_id;
+        rec.src_term = m.src_term;
+        rec.dst_term = m.dst_term;
+        rec.message_id = m.message_id;
+        rec.packet_size = m.packet_size;
+        rec.total_size = m.total_size;
+        rec.chunk_id = m.chunk_id;
+        rec.intm_grp_id = m.intm_grp_id;
+        rec.prev_lp = R.r;  // intm_lp_id
+        rec.prev_port = m.out_port;
+        rec.prev_vc = m.out_vc;
+        rec.last_hop = global ? DFD_HOP_GLOBAL : DFD_HOP_LOCAL;
+        rec.path_type = m.path_type;
+        rec.is_intm_visited = m.is_intm_visited;
+        rec.n_hop = m.n_hop;
+        rec.l_hop = m.l_hop;
+        rec.g_hop = m.g_hop;
+        rec.hops_cur_group = m.hops_cur_group;
+        rec.flags = m.flags;
+        rec.pad0 = 0;
+        rec.travel_start_time = m.travel_start_time;
+        rec.msg_start_time = m.msg_start_time;
+        rec.origin_router = m.origin_router;
+        rec.src_svr = m.src_svr;
+        rec.dst_svr = m.dst_svr;
+        rec.pad1 = 0;
+        if (to_terminal)
+            push_chunk_to_node(c, m.next_stop, rec);
+        else
+            push_chunk_to_router(c, m.next_stop, rec);
+    }
+    if (((m.packet_size % P.chunk_size) || m.packet_size == 0) && (m.chunk_id == nchunks - 1))
+        ps.link_traffic += (m.packet_size % P.chunk_size);
+    else
+        ps.link_traffic += P.chunk_size;
+    ps.total_chunks++;
+    fifo_pop(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan]);
+    R.pool[slot].next = R.h->pool_free;  // free the slot
+    R.h->pool_free = slot;
+    R.h->pool_used--;
+    ps.noat -= P.router_delay;
+    injection_ts -= P.router_delay;
+    int next_output_chan = -1;
+    for (int k = 0; k < DFD_NUM_VCS; k++)
+        if (pq.pend_head[k] != NIL) {
+            next_output_chan = k;
+            break;
+        }
+    if (next_output_chan < 0) {
+        ps.in_send_loop = 0;
+        return;
+    }
+    rheap_push(c, R, now + injection_ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
+}
+
+// router_buf_update dally:8069-8145
+__device__ void router_buf_update(Ctx& c, RCtx& R, double now, int indx, int output_chan) {
+    const DfdParams& P = *c.P;
+    PortState& ps = R.port[indx];
+    PortQ& pq = R.pq[indx];
+    ps.vc_occ[output_chan] -= P.chunk_size;
+    if (ps.last_buf_full > 0.0) {
+        ps.busy_time += (now - ps.last_buf_full);
+        ps.last_buf_full = 0.0;
+    }
+    if (pq.queue_head[output_chan] != NIL) {
+        unsigned slot = fifo_pop(R.pool, &pq.queue_head[output_chan], &pq.queue_tail[output_chan]);
+        PoolSlot& hd = R.pool[slot];
+        router_credit_send(c, R, now, hd.last_hop, hd.prev_lp, hd.prev_port, hd.prev_vc);
+        fifo_append(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan], slot);
+        ps.vc_occ[output_chan] += P.chunk_size;
+        ps.queued_count -= P.chunk_size;
+    }
+    if (ps.in_send_loop == 0 && pq.pend_head[output_chan] != NIL) {
+        double ts = maxd(ps.noat, now) - now;
+        rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)indx);
+        ps.in_send_loop = 1;
+    }
+}
+
+__device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned ntail_k) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    RCtx R;
+    R.r = r;
+    R.gid = rtr_gid(P, r);
+    R.lid = r % P.a;
+    R.grp = r / P.a;
+    R.h = &A.rh[r];
+    R.port = &A.port[(size_t)r * P.radix];
+    R.pq = &A.portq[(size_t)r * P.radix];
+    R.pool = &A.pool[(size_t)r * P.rpool_cap];
+    R.heap = &A.rheap[(size_t)r * P.rheap_cap];
+    // drain the inbox filled during the previous window: chunks go to pool slots, keys to the heap
+    if (ntail_c) {
+        const ChunkRec* in = &A.rcin[((size_t)c.cur * P.NR + r) * P.rcin_cap];
+        for (unsigned i = 0; i < ntail_c; i++) {
+            unsigned slot = R.h->pool_free;
+            if (slot == NIL) {
+                set_error(A, DFD_ERR_POOL_OVERFLOW, r);
+                break;
+            }
+            R.h->pool_free = R.pool[slot].next;
+            R.h->pool_used++;
+            if (R.h->pool_used > R.h->pool_hwm) R.h->pool_hwm = R.h->pool_used;
+            int4 v0 = __ldcg((const int4*)&in[i]);
+            int4* dst = (int4*)&R.pool[slot];
+#pragma unroll
+            for (int k = 1; k < 6; k++) dst[k] = __ldcg((const int4*)&in[i] + k);
+            double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
+            rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CHUNK << 28) | slot);
+        }
+        A.rcin_tail[(size_t)c.cur * P.NR + r] = 0;
+    }
+    if (ntail_k) {
+        const CreditRec* in = &A.rkin[((size_t)c.cur * P.NR + r) * P.rkin_cap];
+        for (unsigned i = 0; i < ntail_k; i++) {
+            int4 v0 = __ldcg((const int4*)&in[i]);
+            int4 v1 = __ldcg((const int4*)&in[i] + 1);
+            double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
+            unsigned port = (unsigned)v1.x & 0xFFFFu, vc = ((unsigned)v1.x >> 16) & 0xFFu;
+            rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CREDIT << 28) | (vc << 16) | port);
+        }
+        A.rkin_tail[(size_t)c.cur * P.NR + r] = 0;
+    }
+    while (R.h->heap_n > 0 && R.heap[0].ts < c.t_end) {
+        RHeapEnt e = rheap_pop(R);
+        double now = e.ts;
+        R.h->events++;
+        unsigned kind = e.ref >> 28;
+        if (kind == RK_CHUNK) {
+            c.ev[EV_R_ARRIVE]++;
+            router_packet_receive(c, R, now, e.ref & 0x0FFFFFFFu);
+        } else if (kind == RK_CREDIT) {
+            c.ev[EV_R_BUFFER]++;
+            router_buf_update(c, R, now, e.ref & 0xFFFFu, (e.ref >> 16) & 0xFFu);
+        } else {
+            c.ev[EV_R_SEND]++;
+            router_packet_send(c, R, now, e.ref & 0xFFFFu);
+        }
+    }
+    double next_ts = R.h->heap_n ? R.heap[0].ts : DINF;
+    A.wake_self[P.NT + r] = d2bits(next_ts);
+    c.cand = fmin(c.cand, next_ts);
+}
+
+// ================================================================================================
+// the window loop
+// ================================================================================================
+__global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, unsigned long long max_windows) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double s_min[DFD_BLOCK / 32];
+    __shared__ unsigned long long s_ev[EV_NTYPES];
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned ttid = threadIdx.x * gridDim.x + blockIdx.x;  // transposed: spreads routers over all blocks
+    Ctx c;
+    c.P = &P;
+    c.A = &A;
+    for (int i = 0; i < EV_NTYPES; i++) c.ev[i] = 0;
+    unsigned long long w = A.counters[1];  // windows executed so far (the kernel may be re-entered)
+    unsigned long long w_stop = w + max_windows;
+    for (;;) {
+        unsigned long long tb = __ldcg(&A.gmin[w % 3]);
+        if (tb >= INF_BITS || __ldcg(&A.counters[2]) != 0 || w >= w_stop) break;
+        double T = bits2d(tb);
+        if (T >= P.ts_end) break;
+        c.t_end = T + P.window;
+        c.cur = (int)(w & 1);
+        c.nxt = c.cur ^ 1;
+        c.cand = DINF;
+        if (gtid == 0) A.gmin[(w + 2) % 3] = INF_BITS;
+        unsigned long long te_bits = d2bits(c.t_end);
+        for (unsigned n = gtid; n < (unsigned)P.NT; n += nthreads) {
+            unsigned long long ws = A.wake_self[n];
+            unsigned long long wi = __ldcg(&A.wake_in[(size_t)c.cur * P.NT + n]);
+            if (wi != INF_BITS) {
+                A.wake_in[(size_t)c.cur * P.NT + n] = INF_BITS;
+                if (wi < ws) {
+                    ws = wi;
+                    A.wake_self[n] = ws;
+                }
+            }
+            if (ws < te_bits)
+                node_process(c, n);
+            else
+                c.cand = fmin(c.cand, bits2d(ws));
+        }
+        for (unsigned r = ttid; r < (unsigned)P.NR; r += nthreads) {
+            unsigned long long ws = A.wake_self[P.NT + r];
+            unsigned tc = __ldcg(&A.rcin_tail[(size_t)c.cur * P.NR + r]);
+            unsigned tk = __ldcg(&A.rkin_tail[(size_t)c.cur * P.NR + r]);
+            if (tc | tk | (unsigned)(ws < te_bits))
+                router_process(c, r, tc, tk);
+            else
+                c.cand = fmin(c.cand, bits2d(ws));
+        }
+        // block-min of the candidates, one atomicMin per block, then the grid barrier that closes the window
+        double v = c.cand;
+        for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double m = s_min[0];
+            for (int i = 1; i < DFD_BLOCK / 32; i++) m = fmin(m, s_min[i]);
+            if (d2bits(m) != INF_BITS) atomicMin(&A.gmin[(w + 1) % 3], d2bits(m));
+        }
+        grid.sync();
+        w++;
+    }
+    // fold the per-thread event counters
+    if (threadIdx.x < EV_NTYPES) s_ev[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = 0; i < EV_NTYPES; i++)
+        if (c.ev[i]) atomicAdd(&s_ev[i], c.ev[i]);
+    __syncthreads();
+    if (threadIdx.x < EV_NTYPES && s_ev[threadIdx.x]) {
+        atomicAdd(&A.counters[4 + threadIdx.x], s_ev[threadIdx.x]);
+        atomicAdd(&A.counters[0], s_ev[threadIdx.x]);
+    }
+    if (gtid == 0) A.counters[1] = w;
+}
+
+// ================================================================================================
+// state initialisation (device side: nothing but scalars crosses PCIe)
+// ================================================================================================
+__device__ unsigned long long mulmod_u64(unsigned long long a, unsigned long long b, unsigned long long m) { return (a * b) % m; }  // a,b < 2^31
+__device__ void seed_stream(int32_t* s, unsigned long long stream, const DfdSeedConsts& K) {
+    for (int j = 0; j < 4; j++) {
+        unsigned long long base = K.avw[j], acc = 1, e = stream, m = K.m[j];
+        while (e) {
+            if (e & 1) acc = mulmod_u64(acc, base, m);
+            base = mulmod_u64(base, base, m);
+            e >>= 1;
+        }
+        s[j] = (int32_t)mulmod_u64(acc, K.seed0[j], m);
+    }
+}
+
+__global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid == 0) {
+        A.gmin[0] = d2bits(P.mean_interval);
+        A.gmin[1] = INF_BITS;
+        A.gmin[2] = INF_BITS;
+        for (int i = 0; i < 4 + EV_NTYPES; i++) A.counters[i] = 0;
+    }
+    for (unsigned n = gtid; n < (unsigned)P.NT; n += nthreads) {
+        NodeState* s = &A.node[n];
+        memset(s, 0, sizeof(NodeState));
+        unsigned sg = svr_gid(P, n), tg = term_gid(P, n);
+        seed_stream(s->rng_svr0, (unsigned long long)sg * 3 + 0, K);
+        seed_stream(s->rng_svr2, (unsigned long long)sg * 3 + 2, K);
+        seed_stream(s->rng_term2, (unsigned long long)tg * 3 + 2, K);
+        s->dest_id = -1;
+        s->min_latency = 2147483647.0;  // INT_MAX dally:4766
+        // svr_init synthetic:287-298: first KICKOFF at mean_interval
+        NodeEv* ev = &A.nev[(size_t)n * P.nev_cap];
+        ev->ts = 0.0 + P.mean_interval;
+        ev->src = sg;
+        ev->seq = s->svr_seq++;
+        ev->type = EV_KICKOFF;
+        s->nev = 1;
+        s->nev_hwm = 1;
+        A.wake_self[n] = d2bits(ev->ts);
+        A.wake_in[n] = INF_BITS;
+        A.wake_in[(size_t)P.NT + n] = INF_BITS;
+        A.ncin_tail[n] = 0;
+        A.nkin_tail[n] = 0;
+        A.ack_count[n] = 0;
+        A.ack_first[n] = INF_BITS;
+        A.ack_last[n] = 0;
+        for (int i = 0; i < P.ncin_cap; i++) *(unsigned long long*)&A.ncin[(size_t)n * P.ncin_cap + i].ts = INF_BITS;
+        for (int i = 0; i < P.nkin_cap; i++) *(unsigned long long*)&A.nkin[(size_t)n * P.nkin_cap + i].ts = INF_BITS;
+    }
+    for (unsigned r = gtid; r < (unsigned)P.NR; r += nthreads) {
+        RouterHdr* h = &A.rh[r];
+        memset(h, 0, sizeof(RouterHdr));
+        seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
+        h->pool_free = 0;
+        A.wake_self[P.NT + r] = INF_BITS;
+        A.rcin_tail[r] = 0;
+        A.rcin_tail[(size_t)P.NR + r] = 0;
+        A.rkin_tail[r] = 0;
+        A.rkin_tail[(size_t)P.NR + r] = 0;
+    }
+    // per-port state and pool free lists, flat over all routers
+    size_t nports = (size_t)P.NR * P.radix;
+    for (size_t i = gtid; i < nports; i += nthreads) {
+        PortState* ps = &A.port[i];
+        memset(ps, 0, sizeof(PortState));
+        PortQ* pq = &A.portq[i];
+        for (int v = 0; v < DFD_NUM_VCS; v++) pq->pend_head[v] = pq->pend_tail[v] = pq->queue_head[v] = pq->queue_tail[v] = NIL;
+    }
+    size_t nslots = (size_t)P.NR * P.rpool_cap;
+    for (size_t i = gtid; i < nslots; i += nthreads) {
+        unsigned k = (unsigned)(i % P.rpool_cap);
+        A.pool[i].next = (k + 1 < (unsigned)P.rpool_cap) ? k + 1 : NIL;
+    }
+}
+
+// ================================================================================================
+// host side of the device engine
+// ================================================================================================
+#define CK(x)                                                                                          \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess) {                                                                       \
+            snprintf(dev->error, sizeof dev->error, "%s failed: %s", #x, cudaGetErrorString(e_));      \
+            return 1;                                                                                  \
+        }                                                                                              \
+    } while (0)
+
+template <typename T> static int dalloc(DfdDevice* dev, T** p, size_t n) {
+    size_t bytes = n * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    CK(cudaMalloc((void**)p, bytes));
+    dev->allocs.push_back((void*)*p);
+    dev->bytes_allocated += bytes;
+    return 0;
+}
+
+int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) {
+    dev->P = P;
+    DfdArrays& A = dev->A;
+    memset(&A, 0, sizeof A);
+    int devid = 0;
+    CK(cudaGetDevice(&devid));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, devid));
+    dev->num_sms = prop.multiProcessorCount;
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, devid));
+    if (!coop) {
+        snprintf(dev->error, sizeof dev->error, "device does not support cooperative launch");
+        return 1;
+    }
+    size_t NT = P.NT, NR = P.NR, NLP = NT + NR;
+    if (dalloc(dev, &A.wake_self, NLP)) return 1;
+    if (dalloc(dev, &A.wake_in, 2 * NT)) return 1;
+    if (dalloc(dev, &A.gmin, 4)) return 1;
+    if (dalloc(dev, &A.node, NT)) return 1;
+    if (dalloc(dev, &A.nev, NT * P.nev_cap)) return 1;
+    if (dalloc(dev, &A.sq, NT * P.nsq_cap)) return 1;
+    if (dalloc(dev, &A.tq, NT * P.ntq_cap)) return 1;
+    if (dalloc(dev, &A.ncin, NT * P.ncin_cap)) return 1;
+    if (dalloc(dev, &A.nkin, NT * P.nkin_cap)) return 1;
+    if (dalloc(dev, &A.ncin_tail, NT)) return 1;
+    if (dalloc(dev, &A.nkin_tail, NT)) return 1;
+    if (dalloc(dev, &A.ack_count, NT)) return 1;
+    if (dalloc(dev, &A.ack_first, NT)) return 1;
+    if (dalloc(dev, &A.ack_last, NT)) return 1;
+    if (dalloc(dev, &A.rh, NR)) return 1;
+    if (dalloc(dev, &A.port, NR * P.radix)) return 1;
+    if (dalloc(dev, &A.portq, NR * P.radix)) return 1;
+    if (dalloc(dev, &A.pool, NR * P.rpool_cap)) return 1;
+    if (dalloc(dev, &A.rheap, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.rcin, 2 * NR * P.rcin_cap)) return 1;
+    if (dalloc(dev, &A.rkin, 2 * NR * P.rkin_cap)) return 1;
+    if (dalloc(dev, &A.rcin_tail, 2 * NR)) return 1;
+    if (dalloc(dev, &A.rkin_tail, 2 * NR)) return 1;
+    if (dalloc(dev, &A.counters, 32)) return 1;
+    int *loc_off, *loc_port, *loc_dest, *gs_port, *gs_group, *gdest, *routed_off, *routed_lid;
+    if (dalloc(dev, &loc_off, T.loc_off.size())) return 1;
+    if (dalloc(dev, &loc_port, T.loc_port.size())) return 1;
+    if (dalloc(dev, &loc_dest, T.loc_dest.size())) return 1;
+    if (dalloc(dev, &gs_port, T.gs_port.size())) return 1;
+    if (dalloc(dev, &gs_group, T.gs_group.size())) return 1;
+    if (dalloc(dev, &gdest, T.gdest.size())) return 1;
+    if (dalloc(dev, &routed_off, T.routed_off.size())) return 1;
+    if (dalloc(dev, &routed_lid, T.routed_lid.size())) return 1;
+    A.loc_off = loc_off;
+    A.loc_port = loc_port;
+    A.loc_dest = loc_dest;
+    A.gs_port = gs_port;
+    A.gs_group = gs_group;
+    A.gdest = gdest;
+    A.routed_off = routed_off;
+    A.routed_lid = routed_lid;
+    dev->topo_bytes = 0;
+    // grid: persistent, co-resident (cooperative launch)
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfd_run_kernel, DFD_BLOCK, 0));
+    if (per_sm < 1) {
+        snprintf(dev->error, sizeof dev->error, "run kernel does not fit on an SM");
+        return 1;
+    }
+    size_t want = (std::max(NT, NR) + DFD_BLOCK - 1) / DFD_BLOCK;
+    size_t maxb = (size_t)per_sm * dev->num_sms;
+    dev->grid = (int)std::max<size_t>(1, std::min(want, maxb));
+    dev->blocks_per_sm = per_sm;
+    return 0;
+}
+
+int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st) {
+    DfdArrays& A = dev->A;
+    size_t total = 0;
+#define UP(dst, vec)                                                                                         \
+    do {                                                                                                     \
+        if (!(vec).empty()) CK(cudaMemcpyAsync((void*)(dst), (vec).data(), (vec).size() * sizeof(int), cudaMemcpyHostToDevice, st)); \
+        total += (vec).size() * sizeof(int);                                                                 \
+    } while (0)
+    UP(A.loc_off, T.loc_off);
+    UP(A.loc_port, T.loc_port);
+    UP(A.loc_dest, T.loc_dest);
+    UP(A.gs_port, T.gs_port);
+    UP(A.gs_group, T.gs_group);
+    UP(A.gdest, T.gdest);
+    UP(A.routed_off, T.routed_off);
+    UP(A.routed_lid, T.routed_lid);
+#undef UP
+    dev->topo_bytes = total;
+    return 0;
+}
+
+int dfd_device_reset(DfdDevice* dev, cudaStream_t st) {
+    int blocks = dev->num_sms * 8;
+    dfd_init_kernel<<<blocks, 256, 0, st>>>(dev->P, dev->A, dev->seeds);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windows) {
+    void* args[] = {(void*)&dev->P, (void*)&dev->A, (void*)&max_windows};
+    CK(cudaLaunchCooperativeKernel((void*)dfd_run_kernel, dim3(dev->grid), dim3(DFD_BLOCK), args, 0, st));
+    return 0;
+}
+
+int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st) {
+    const DfdParams& P = dev->P;
+    const DfdArrays& A = dev->A;
+    out->node.resize(P.NT);
+    out->rh.resize(P.NR);
+    out->port.resize((size_t)P.NR * P.radix);
+    out->ack_count.resize(P.NT);
+    out->ack_first.resize(P.NT);
+    out->ack_last.resize(P.NT);
+    CK(cudaMemcpyAsync(out->node.data(), A.node, sizeof(NodeState) * P.NT, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->rh.data(), A.rh, sizeof(RouterHdr) * P.NR, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->port.data(), A.port, sizeof(PortState) * P.NR * P.radix, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->ack_count.data(), A.ack_count, sizeof(unsigned) * P.NT, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->ack_first.data(), A.ack_first, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->ack_last.data(), A.ack_last, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->d2h_bytes = sizeof(NodeState) * (size_t)P.NT + sizeof(RouterHdr) * (size_t)P.NR + sizeof(PortState) * (size_t)P.NR * P.radix +
+                     (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * (size_t)P.NT + sizeof(unsigned long long) * 32;
+    return 0;
+}
+
+int dfd_device_read_counters(DfdDevice* dev, unsigned long long* counters, cudaStream_t st) {
+    CK(cudaMemcpyAsync(counters, dev->A.counters, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+void dfd_device_destroy(DfdDevice* dev) {
+    for (void* p : dev->allocs) cudaFree(p);
+    dev->allocs.clear();
+}
