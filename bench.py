@@ -1,0 +1,233 @@
+#!/usr/bin/env python3
+"""bench.py -- committed events/s of the dragonfly-dally hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one complete simulation of the workload (BASELINE.json configs[1]: dragonfly-dally 1,056
+terminals, a=8 p=4 h=4 g=33, uniform-random traffic, minimal routing, default credit delay): every LP's
+state is re-initialised on the device, then the window kernel runs the event loop to completion.
+  value      committed events / s, device-timed (CUDA events on the launching stream) over the window kernel,
+             LP state and connection tables already resident in HBM
+  e2e        the same metric through the C-ABI call sequence of the reference's main() with host buffers:
+             table upload (H2D) + device init + event loop + statistics download (D2H) + *_final handlers
+  roofline   algorithmic bytes (832*sum(N_hop) + 896*N_chunks per run) / kernel time vs the
+             measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (single-threaded restatement of the reference handlers) on the same workload
+--impl reference times that CPU implementation alone (the reference itself needs ROSS + MPI, absent here).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(conf=os.path.join(ROOT, "configs", "dfdally-1056.conf"), traffic=1, num_messages=100, payload_sz=2048)
+WORKLOAD_NAME = "dragonfly-dally 1,056-terminal (a=8,p=4,h=4,g=33) uniform-random, minimal routing, 100 msgs/terminal x 2048 B, arrival 1000 ns"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 6 and f[0].isdigit():
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(int(r[0]) for r in self.rows), "sm_max_mhz": int(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def algorithmic_bytes(total_hops, chunks):
+    return 832 * total_hops + 896 * chunks
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation of the path = the oracle port (ROSS/MPI are not buildable here)."""
+    if rank != 0:
+        return
+    from tests import oracle_util
+    oracle_util.load()
+    w = dict(WORKLOAD)
+    conf = w.pop("conf")
+    for _ in range(args.warmup):
+        oracle_util.run(conf, **w)
+    t0 = time.perf_counter()
+    events = packets = 0
+    loop = 0.0
+    for _ in range(args.steps):
+        r = oracle_util.run(conf, **w)
+        events += r.events
+        packets += r.finished_packets
+        loop += r.run_seconds
+    wall = time.perf_counter() - t0
+    value = events / loop
+    line = {"metric": "committed events/sec", "value": value, "unit": "events/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "packets_per_s": packets / loop,
+                       "note": "event loop only (config parsing / table construction excluded); wall incl. setup %.3f s" % wall},
+            "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": "port",
+                             "sample": "the full workload, %d run(s): single-threaded sequential event loop (restated reference handlers, "
+                                       "not ROSS: ROSS+MPI are external and absent)" % args.steps},
+            "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import codes_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the dragonfly-dally engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = dict(WORKLOAD)
+    conf = w.pop("conf")
+    opts = codes_b200.make_opts(**w)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    eng = codes_b200.Engine()
+    eng.setup(conf, opts)
+    eng.upload(stream)
+
+    def one_step(timed):
+        eng.reset(stream)
+        flush.fill_(1)  # evict LP state from L2 between steps
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.run(stream)
+            e1.record()
+            return e0, e1
+        eng.run(stream)
+        return None
+
+    for _ in range(max(args.warmup, 0)):
+        one_step(False)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [one_step(True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
+    eng.finish(stream)
+    s = eng.summary()
+    events_per_step, packets_per_step = s.events, s.finished_packets
+    hops, chunks, windows = s.total_hops, s.finished_chunks, s.windows
+
+    # e2e: the reference's main() call sequence, host buffers on both sides, H2D + D2H inside the timed region
+    e2e_eng = codes_b200.Engine()
+    e2e_eng.setup(conf, opts)
+    e2e_eng.tw_run(stream)  # warm (allocations, module load)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_eng.tw_run(stream)
+    e2e_s = time.perf_counter() - t0
+    es = e2e_eng.summary()
+    assert es.events == events_per_step
+
+    t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    kernel_ms, e2e_s = float(t[0]), float(t[1])
+    total_events = events_per_step * args.steps * world  # N independent replicas of the workload (see config.parallelism)
+    value = total_events / (kernel_ms * 1e-3)
+    peak, peak_src = peaks()
+    ach = algorithmic_bytes(hops, chunks) * args.steps / (kernel_ms * 1e-3) / 1e9
+    line = {"metric": "committed events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME, "events_per_step": events_per_step, "packets_per_step": packets_per_step,
+                       "packets_per_s": packets_per_step * args.steps * world / (kernel_ms * 1e-3),
+                       "windows_per_step": windows, "window_ns": s.window_ns, "us_per_window": 1e3 * kernel_ms / args.steps / max(windows, 1),
+                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                       "grid": [s.grid_blocks, s.block_threads], "device_bytes": s.device_bytes,
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (group-sharded exchange not built yet)"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step)",
+                         "note": "the kernel is bound by per-window latency (grid barrier + dependent loads), not by HBM bandwidth"},
+            "e2e": {"value": events_per_step * args.steps * world / e2e_s, "unit": "events/s", "h2d_bytes_per_step": es.h2d_bytes,
+                    "d2h_bytes_per_step": es.d2h_bytes, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": 2 * args.steps, "clocks": clocks}
+    if rank == 0 and not args.no_cpu_baseline:
+        from tests import oracle_util
+        oracle_util.load()
+        r = oracle_util.run(conf, **w)
+        assert r.events == events_per_step, (r.events, events_per_step)
+        line["cpu_baseline"] = {"value": r.events / r.run_seconds, "unit": "events/s", "cores": 1, "kind": "port",
+                                "sample": "the full workload once (%d events, %.2f s): single-threaded sequential event loop over "
+                                          "the restated reference handlers; ROSS itself is external and not buildable here" % (r.events, r.run_seconds)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

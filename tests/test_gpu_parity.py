@@ -1,0 +1,153 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI, against the CPU oracle on the same config and
+seed.  Bit-exact bar: every lp-io file (integer columns and %lf columns) and the hex-float raw statistics
+must be byte-identical; `Net Events Processed` must be equal."""
+import hashlib
+import json
+import os
+
+import pytest
+
+import codes_b200
+from tests import oracle_util
+from tests.test_oracle_cpu import CONF72, CONF1056, CONF8K, GOLDEN, GOLDEN_CASES, parse_cn_stats, parse_link_stats
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(tmp_path, conf, **opts):
+    gdir, odir = str(tmp_path / "gpu"), str(tmp_path / "oracle")
+    s = codes_b200.run_synthetic(conf, lp_io_dir=gdir, **opts)
+    o = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    return s, o, oracle_util.read_dir(gdir), oracle_util.read_dir(odir)
+
+
+def assert_identical(s, o, g, r):
+    assert s.events == o.events
+    for i, name in enumerate(oracle_util.EV_NAMES):
+        assert s.events_by_type[i] == o.ev_by_type[i], name
+    assert (s.finished_packets, s.finished_chunks, s.finished_msgs, s.total_hops) == \
+           (o.finished_packets, o.finished_chunks, o.finished_msgs, o.total_hops)
+    assert (s.minimal_count, s.nonmin_count) == (o.minimal_count, o.nonmin_count)
+    assert s.rng_draws == o.rng_draws
+    assert s.total_time == o.total_time and s.max_latency == o.max_latency  # exact doubles
+    assert s.svr_sum_latency == o.svr_sum_latency and s.max_end_ts == o.max_end_ts
+    assert sorted(g) == sorted(r)
+    for name in r:
+        assert g[name] == r[name], f"{name} differs"
+
+
+CASES = [
+    ("72-m1", CONF72, dict(num_messages=1)),                       # the reference's own test case
+    ("72-m20", CONF72, dict(num_messages=20)),                      # driver default
+    ("72-nearest-group", CONF72, dict(num_messages=10, traffic=3)),  # congested: overflow queues, stalls, busy time
+    ("72-nearest-neighbor", CONF72, dict(num_messages=10, traffic=4)),
+    ("72-rand-perm", CONF72, dict(num_messages=10, traffic=2)),      # includes self-sends (noop path)
+    ("72-random-other-group", CONF72, dict(num_messages=5, traffic=5)),
+    ("72-high-load", CONF72, dict(num_messages=30, arrival_time=200.0)),  # injection throttling (issueIdle)
+    ("72-load-per-svr", CONF72, dict(num_messages=10, load_per_svr=0.5)),
+    ("72-small-payload", CONF72, dict(num_messages=10, payload_sz=8)),
+    ("72-full-chunk", CONF72, dict(num_messages=10, payload_sz=4096)),
+    ("72-warmup", CONF72, dict(num_messages=10, warm_up_time=3000.0)),
+    ("72-end-time", CONF72, dict(num_messages=20, end_time=12000.0)),  # events past --end are dropped
+    ("1056-uniform", CONF1056, dict(num_messages=10)),
+    ("1056-nearest-group", CONF1056, dict(num_messages=5, traffic=3)),
+    ("8320-par-uniform", CONF8K, dict(num_messages=3)),
+    ("8320-par-nearest-group", CONF8K, dict(num_messages=3, traffic=3)),  # PAR takes non-minimal paths
+]
+
+
+@pytest.mark.parametrize("name,conf,opts", CASES, ids=[c[0] for c in CASES])
+def test_engine_matches_oracle(tmp_path, name, conf, opts):
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)
+
+
+def variant_conf(tmp_path, base, name, **params):
+    with open(base) as f:
+        text = f.read()
+    d = os.path.dirname(base)
+    stem = os.path.basename(base)[:-5]
+    text = text.replace(f'"{stem}-intra"', f'"{d}/{stem}-intra"').replace(f'"{stem}-inter"', f'"{d}/{stem}-inter"')
+    for k, v in params.items():
+        if f"{k}=" in text:
+            import re
+            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}="{v}";', text, flags=re.M)
+        else:
+            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}="{v}";')
+    p = tmp_path / (name + ".conf")
+    p.write_text(text)
+    return str(p)
+
+
+VARIANTS = [
+    ("72-nonminimal", CONF72, dict(routing="nonminimal"), dict(num_messages=10)),
+    ("72-par", CONF72, dict(routing="prog-adaptive", adaptive_threshold="0"), dict(num_messages=20, traffic=3)),
+    ("72-par-alpha", CONF72, dict(routing="prog-adaptive", route_scoring_metric="alpha"), dict(num_messages=20, arrival_time=300.0)),
+    ("72-credit-delay-100", CONF72, dict(credit_delay="100"), dict(num_messages=20)),  # wider lookahead window
+    ("72-tiny-vcs", CONF72, dict(local_vc_size="4096", global_vc_size="4096", cn_vc_size="4096"), dict(num_messages=10)),
+    ("72-asym-bw", CONF72, dict(local_bandwidth="5.25", global_bandwidth="4.7", cn_bandwidth="8.0", router_delay="50"), dict(num_messages=10)),
+    ("1056-nonminimal", CONF1056, dict(routing="nonminimal"), dict(num_messages=4)),
+    ("1056-par", CONF1056, dict(routing="prog-adaptive", adaptive_threshold="16384"), dict(num_messages=6, traffic=3)),
+]
+
+
+@pytest.mark.parametrize("name,base,params,opts", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_engine_matches_oracle_config_variants(tmp_path, name, base, params, opts):
+    conf = variant_conf(tmp_path, base, name, **params)
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)
+    if name in ("72-par", "1056-par"):
+        assert s.nonmin_count > 0
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_engine_matches_committed_golden(tmp_path, name):
+    case = dict(GOLDEN_CASES[name])
+    conf = case.pop("conf")
+    gdir = str(tmp_path / "gpu")
+    s = codes_b200.run_synthetic(conf, lp_io_dir=gdir, **case)
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        gold = json.load(f)
+    assert s.events == gold["events"]
+    out = oracle_util.read_dir(gdir)
+    for fname, digest in gold["sha256"].items():
+        assert hashlib.sha256(out[fname]).hexdigest() == digest, fname
+
+
+def test_determinism_and_state_reuse(tmp_path):
+    """Two runs give identical output, and a reset engine (tables kept on the device) repeats it exactly."""
+    a, b, c = str(tmp_path / "a"), str(tmp_path / "b"), str(tmp_path / "c")
+    s1 = codes_b200.run_synthetic(CONF72, lp_io_dir=a, num_messages=12)
+    with codes_b200.Engine() as e:
+        e.setup(CONF72, codes_b200.make_opts(num_messages=12))
+        e.upload()
+        e.run()
+        e.finish()
+        e.lp_io_flush(b)
+        e.reset()
+        e.run()
+        e.finish()
+        e.lp_io_flush(c)
+        assert e.summary().events == s1.events
+        assert "Net Events Processed" in e.model_net_report_stats()
+    assert oracle_util.read_dir(a) == oracle_util.read_dir(b) == oracle_util.read_dir(c)
+
+
+def test_full_size_properties_1056(tmp_path):
+    """BASELINE config[1] at the bench size: size-independent properties (conservation, credit invariants)."""
+    gdir = str(tmp_path / "gpu")
+    msgs = 100
+    s = codes_b200.run_synthetic(CONF1056, lp_io_dir=gdir, num_messages=msgs)
+    n = 1056
+    assert s.packet_gen == s.packet_fin == n * msgs == s.finished_msgs == s.svr_msgs_recvd
+    assert s.minimal_count == s.finished_chunks and s.nonmin_count == 0
+    # committed events: 11 + 3*hops per message + terminating KICKOFF per server + one T_SEND per stalled injection
+    out = oracle_util.read_dir(gdir)
+    links = parse_link_stats(out["dragonfly-link-stats"])
+    stalled_inj = sum(l["stalled"] for l in links if l["st"] == "T")
+    assert s.events == 11 * n * msgs + 3 * s.total_hops + n + stalled_inj
+    assert sum(l["traffic"] for l in links if l["st"] == "T") == 4096 * s.finished_chunks
+    assert sum(l["traffic"] for l in links if l["st"] == "R" and l["dt"] == "T") == 2048 * s.finished_chunks
+    cn = parse_cn_stats(out["dragonfly-cn-stats"])
+    assert sum(r["recvd"] for r in cn) == 2048 * n * msgs
+    assert all(r["avg_hops"] <= 4.0 for r in cn)

@@ -1,0 +1,195 @@
+"""CPU tests of the oracle: known-answer checks derived from the reference's closed forms and
+regression against the committed golden vectors.  No GPU needed."""
+import math
+import os
+import struct
+
+import pytest
+
+from tests import oracle_util
+
+ROOT = oracle_util.ROOT
+CONF72 = os.path.join(ROOT, "configs", "dfdally-72.conf")
+CONF1056 = os.path.join(ROOT, "configs", "dfdally-1056.conf")
+CONF8K = os.path.join(ROOT, "configs", "dfdally-8320-par.conf")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+M = [2147483647, 2147483543, 2147483423, 2147483323]
+A = [45991, 207707, 138556, 49689]
+SEED0 = [11111111, 22222222, 33333333, 44444444]
+
+
+def py_bytes_to_ns(nbytes, bw):
+    t = float(nbytes) / (1024.0 * 1024.0 * 1024.0)
+    t = t / bw
+    return t * 1000.0 * 1000.0 * 1000.0
+
+
+def test_bytes_to_ns_known_answers(oracle):
+    # dragonfly-dally.cxx:1588-1599; the 72-terminal config numbers
+    assert oracle.dfdally_oracle_bytes_to_ns(4096, 2.0) == 1907.3486328125
+    assert oracle.dfdally_oracle_bytes_to_ns(2048, 2.0) == 953.67431640625
+    assert oracle.dfdally_oracle_bytes_to_ns(8, 2.0) == 3.725290298461914
+    for n, bw in [(1, 5.25), (4096, 4.7), (512, 5.25), (123457, 12.5)]:
+        assert oracle.dfdally_oracle_bytes_to_ns(n, bw) == py_bytes_to_ns(n, bw)
+
+
+def test_clcg4_stream_seeding_and_steps():
+    # stream k starts at seed0 * (a^(2^(31+41)))^k mod m  (L'Ecuyer-Andres jump-ahead)
+    for stream in [0, 1, 2, 3, 7, 180 * 3 + 2, 2134080 * 3 + 2]:
+        u, st = oracle_util.rng_stream(stream, 5)
+        exp = [SEED0[j] * pow(pow(A[j], 2 ** 72, M[j]), stream, M[j]) % M[j] for j in range(4)]
+        assert st == exp
+        s = list(exp)
+        for i in range(5):
+            s = [s[j] * A[j] % M[j] for j in range(4)]
+            v = 0.0
+            v = v + 4.65661287524579692e-10 * s[0]
+            v = v - 4.65661310075985993e-10 * s[1]
+            if v < 0:
+                v += 1.0
+            v = v + 4.65661336096842131e-10 * s[2]
+            if v >= 1.0:
+                v -= 1.0
+            v = v - 4.65661357780891134e-10 * s[3]
+            if v < 0:
+                v += 1.0
+            assert u[i] == v
+            assert 0.0 <= u[i] < 1.0
+    # stream 0 is the generator's default seed
+    assert oracle_util.rng_stream(0, 1)[1] == SEED0
+
+
+def parse_cn_stats(blob):
+    rows = []
+    for line in blob.decode().splitlines():
+        if line.startswith("#") or not line.strip():
+            continue
+        f = line.split()
+        rows.append(dict(gid=int(f[0]), tid=int(f[1]), sent=int(f[2]), recvd=int(f[3]), avg_lat=float(f[4]),
+                         max_lat=float(f[5]), min_lat=float(f[6]), packets=int(f[7]), avg_hops=float(f[8]),
+                         busy=float(f[9])))
+    return rows
+
+
+def parse_link_stats(blob):
+    rows = []
+    for line in blob.decode().splitlines():
+        if line.startswith("#") or not line.strip():
+            continue
+        f = line.split()
+        rows.append(dict(src=int(f[0]), st=f[1], dst=int(f[2]), dt=f[3], kind=f[4], traffic=int(f[5]),
+                         busy=float(f[6]), stalled=int(f[7])))
+    return rows
+
+
+def test_single_message_idle_network_latency(tmp_path):
+    """One message per server on an idle 72-terminal network: every chunk latency follows the closed form
+    inj(tail, cn) + cn_delay + hops * (inj(tail) + router_delay + link_delay)  (dally:5898-5916, 7811-7833)."""
+    res = oracle_util.run(CONF72, lp_io_dir=str(tmp_path), num_messages=1)
+    n = 72
+    assert res.packet_gen == n and res.packet_fin == n and res.finished_msgs == n and res.finished_chunks == n
+    # event count: 11 + 3*hops per message + one terminating KICKOFF per server
+    assert res.events == 11 * n + 3 * res.total_hops + n
+    tail = py_bytes_to_ns(2048, 2.0)
+    link = py_bytes_to_ns(4096, 2.0)
+    per_hop = tail + 100.0 + link
+    rows = parse_cn_stats(oracle_util.read_dir(str(tmp_path))["dragonfly-cn-stats"])
+    assert len(rows) == n
+    seen = 0
+    for r in rows:
+        if r["packets"] == 0:
+            assert math.isnan(r["avg_lat"]) and r["min_lat"] == 2147483647.0  # dally:6850-6853, :4766
+            continue
+        seen += r["packets"]
+        for lat in (r["max_lat"], r["min_lat"]):
+            hops = (lat - tail - link) / per_hop
+            # with one message per node a few chunks share a link and wait; the uncontended ones sit on the grid
+            assert hops > 0.99
+        assert 1.0 <= r["avg_hops"] <= 4.0  # minimal routing: at most local-global-local + ejection
+    assert seen == n
+    # the minimum over all terminals is an uncontended chunk: exactly on the closed form
+    best = min(r["min_lat"] for r in rows if r["packets"])
+    hops = round((best - tail - link) / per_hop)
+    assert abs(best - (tail + link + hops * per_hop)) < 1e-6
+
+
+@pytest.mark.parametrize("conf,msgs,traffic", [(CONF72, 20, 1), (CONF72, 5, 3), (CONF72, 5, 2), (CONF1056, 3, 1)])
+def test_conservation_and_credit_invariants(tmp_path, conf, msgs, traffic):
+    res = oracle_util.run(conf, lp_io_dir=str(tmp_path), num_messages=msgs, traffic=traffic)
+    out = oracle_util.read_dir(str(tmp_path))
+    cn = parse_cn_stats(out["dragonfly-cn-stats"])
+    nterm = len(cn)
+    # every generated packet is delivered (dally:3186-3189)
+    assert res.packet_gen == res.packet_fin
+    assert res.svr_msgs_recvd == nterm * msgs
+    if traffic != 2:
+        assert res.packet_gen == nterm * msgs
+    else:
+        # RAND_PERM may draw the sender itself: those messages take model_net_noop_event (model-net.c:252-286)
+        assert res.packet_gen <= nterm * msgs and (nterm * msgs - res.packet_gen) % msgs == 0
+    assert res.finished_msgs == res.packet_gen
+    assert sum(r["sent"] for r in cn) == 2048 * res.packet_gen
+    assert sum(r["recvd"] for r in cn) == 2048 * res.packet_gen
+    links = parse_link_stats(out["dragonfly-link-stats"])
+    # terminals inject one full chunk_size of link traffic per chunk (dally:5975)
+    assert sum(l["traffic"] for l in links if l["st"] == "T") == 4096 * res.finished_chunks
+    # router->terminal ports carry the delivered bytes (tail chunk size, dally:7926-7954)
+    assert sum(l["traffic"] for l in links if l["st"] == "R" and l["dt"] == "T") == 2048 * res.finished_chunks
+    assert res.minimal_count + res.nonmin_count == res.finished_chunks
+    # no "leftover" warnings: all queues drained (dally:6855-6858, 6988-6997) -> summary has none
+    assert b"leftover" not in out["summary.txt"] and b"lefover" not in out["summary.txt"]
+    # hops: minimal routing never exceeds 4 router traversals
+    for r in cn:
+        if r["packets"]:
+            assert r["avg_hops"] <= 4.0 + 1e-9
+
+
+def test_prog_adaptive_runs_and_uses_nonminimal_paths(tmp_path):
+    res = oracle_util.run(CONF8K, lp_io_dir=str(tmp_path), num_messages=2, traffic=3)  # worst-case group permutation
+    assert res.packet_fin == 8320 * 2
+    assert res.nonmin_count > 0  # PAR diverts around the single minimal global link
+    assert res.minimal_count + res.nonmin_count == res.finished_chunks
+
+
+def test_determinism_two_runs_identical(tmp_path):
+    # the reference's own test strategy: two runs of the same config are identical (tests/CMakeLists.txt:654-660)
+    a, b = tmp_path / "a", tmp_path / "b"
+    r1 = oracle_util.run(CONF72, lp_io_dir=str(a), num_messages=7)
+    r2 = oracle_util.run(CONF72, lp_io_dir=str(b), num_messages=7)
+    assert r1.events == r2.events
+    assert oracle_util.read_dir(str(a)) == oracle_util.read_dir(str(b))
+
+
+GOLDEN_CASES = {
+    "72_uniform_m1": dict(conf=CONF72, num_messages=1, traffic=1),
+    "72_uniform_m20": dict(conf=CONF72, num_messages=20, traffic=1),
+    "72_nearest_group_m10": dict(conf=CONF72, num_messages=10, traffic=3),
+    "1056_uniform_m5": dict(conf=CONF1056, num_messages=5, traffic=1),
+    "8320_par_uniform_m2": dict(conf=CONF8K, num_messages=2, traffic=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_oracle_matches_golden(tmp_path, name):
+    import hashlib
+    import json
+    case = dict(GOLDEN_CASES[name])
+    conf = case.pop("conf")
+    res = oracle_util.run(conf, lp_io_dir=str(tmp_path), **case)
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        gold = json.load(f)
+    assert res.events == gold["events"]
+    out = oracle_util.read_dir(str(tmp_path))
+    for fname, digest in gold["sha256"].items():
+        assert hashlib.sha256(out[fname]).hexdigest() == digest, fname
+    small = os.path.join(GOLDEN, name)
+    if os.path.isdir(small):
+        for fname in os.listdir(small):
+            with open(os.path.join(small, fname), "rb") as f:
+                assert out[fname] == f.read(), fname
+
+
+def test_config_errors():
+    with pytest.raises(oracle_util.OracleError):
+        oracle_util.run("/nonexistent.conf")
