@@ -47,7 +47,9 @@ class Summary(ctypes.Structure):
                 ("h2d_bytes", ctypes.c_ulonglong), ("d2h_bytes", ctypes.c_ulonglong),
                 ("device_bytes", ctypes.c_ulonglong),
                 ("grid_blocks", ctypes.c_int), ("block_threads", ctypes.c_int), ("num_sms", ctypes.c_int),
-                ("num_terminals", ctypes.c_int), ("num_routers", ctypes.c_int), ("radix", ctypes.c_int)]
+                ("num_terminals", ctypes.c_int), ("num_routers", ctypes.c_int), ("radix", ctypes.c_int),
+                ("cyc_scan", ctypes.c_double), ("cyc_process", ctypes.c_double), ("cyc_barrier", ctypes.c_double),
+                ("cyc_process_max_block", ctypes.c_double), ("cyc_process_longest", ctypes.c_double)]
 
     def as_dict(self):
         d = {}

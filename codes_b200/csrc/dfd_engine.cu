@@ -19,14 +19,13 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (timestamps must be plain IEEE double
 // operations in the reference's order, so FMA contraction is disabled for the whole file).
 
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dfd_engine.h"
 
-namespace cg = cooperative_groups;
 
 #define INF_BITS 0x7FF0000000000000ULL
 #define NIL 0xFFFFFFFFu
@@ -42,8 +41,16 @@ struct Ctx {
     double t_end;
     double cand;  // min timestamp of everything this thread left pending or pushed this window
     int cur, nxt;
-    unsigned long long ev[EV_NTYPES];
+    unsigned* ev;  // per-block event counters by type (shared memory)
 };
+#define COUNT_EV(c, t) atomicAdd(&(c).ev[t], 1u)
+#ifdef DFD_PROFILE
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(c, t) atomicAdd(&(c).A->counters[32 + (t)], (unsigned long long)(clock64() - prof_t0))
+#else
+#define PROF_T0()
+#define PROF_ADD(c, t)
+#endif
 
 __device__ __forceinline__ void set_error(const DfdArrays& A, unsigned code, unsigned long long info) {
     if (atomicCAS(&A.counters[2], 0ULL, (unsigned long long)code) == 0ULL) A.counters[3] = info;
@@ -98,6 +105,16 @@ __device__ __forceinline__ double bytes_to_ns(unsigned long long bytes, double G
     return time;
 }
 __device__ __forceinline__ double maxd(double a, double b) { return a < b ? b : a; }
+// exact n / d for n < 2^32 via the precomputed reciprocal (magic == 0 encodes d == 1)
+__device__ __forceinline__ unsigned fastdiv(unsigned n, unsigned long long magic) { return magic ? (unsigned)__umul64hi((unsigned long long)n, magic) : n; }
+// bytes_to_ns(bytes, bw) for bw in {cn, local, global}: the two sizes every chunk of this workload uses are precomputed
+enum { BW_CN = 0, BW_LOCAL = 1, BW_GLOBAL = 2 };
+__device__ __forceinline__ double inj_delay(const DfdParams& P, unsigned bytes, int which) {
+    if (bytes == (unsigned)P.chunk_size) return which == BW_CN ? P.inj_chunk_cn : which == BW_LOCAL ? P.inj_chunk_local : P.inj_chunk_global;
+    if (bytes == (unsigned)P.payload_sz % (unsigned)P.chunk_size) return which == BW_CN ? P.inj_pay_cn : which == BW_LOCAL ? P.inj_pay_local : P.inj_pay_global;
+    return bytes_to_ns(bytes, which == BW_CN ? P.cn_bw : which == BW_LOCAL ? P.local_bw : P.global_bw);
+}
+__device__ __forceinline__ unsigned mod_chunk(unsigned x, unsigned chunk) { return x < chunk ? x : x % chunk; }
 
 // gid arithmetic (codes_mapping.c:149-378 collapsed to closed forms)
 __device__ __forceinline__ unsigned svr_gid(const DfdParams& P, unsigned k) { return (k / P.p) * P.lps_per_rep + P.off_svr + k % P.p; }
@@ -161,10 +178,12 @@ __device__ void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
     if (rec.ts >= P.ts_end) return;
     unsigned idx = A.ncin_tail[n]++;
     ChunkRec* slot = &A.ncin[(size_t)n * P.ncin_cap + (idx & (P.ncin_cap - 1))];
+#ifdef DFD_CHECKED
     if (d2bits(__ldcg(&slot->ts)) != INF_BITS) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, 0x80000000u | n);
         return;
     }
+#endif
     int4* dst = (int4*)slot;
     const int4* src = (const int4*)&rec;
 #pragma unroll
@@ -178,10 +197,12 @@ __device__ void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src,
     if (ts >= P.ts_end) return;
     unsigned idx = A.nkin_tail[n]++;
     CreditRec* slot = &A.nkin[(size_t)n * P.nkin_cap + (idx & (P.nkin_cap - 1))];
+#ifdef DFD_CHECKED
     if (d2bits(__ldcg(&slot->ts)) != INF_BITS) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, 0xC0000000u | n);
         return;
     }
+#endif
     CreditRec rec;
     rec.ts = ts;
     rec.src = src;
@@ -228,7 +249,7 @@ __device__ __forceinline__ double node_cll(const DfdParams& P, NodeState* s, int
 // issue_event synthetic:231-271: next KICKOFF at now + mean_interval
 __device__ __forceinline__ void svr_issue_event(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now) {
     const DfdParams& P = *c.P;
-    node_add_event(c, n, s, list, now + P.mean_interval, svr_gid(P, n), s->svr_seq++, EV_KICKOFF);
+    node_add_event(c, n, s, list, now + P.mean_interval, s->svr_gid, s->svr_seq++, EV_KICKOFF);
 }
 
 // handle_kickoff_event synthetic:329-413 + model_net_event_impl_base model-net.c:288-380
@@ -238,11 +259,14 @@ __device__ void svr_kickoff(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doub
     long long local_dest = -1;
     if (P.traffic == DFD_TR_UNIFORM) {
         local_dest = clcg4_integer(s->rng_svr0, 1, (long long)P.num_nodes - 2, &s->rng_draws);
-        local_dest = ((long long)n + local_dest) % P.num_nodes;
+        local_dest = (long long)n + local_dest;  // (svr_id + d) % num_nodes with d < num_nodes
+        if (local_dest >= P.num_nodes) local_dest -= P.num_nodes;
     } else if (P.traffic == DFD_TR_NEAREST_GROUP) {
-        local_dest = ((long long)n + P.nodes_per_grp) % P.num_nodes;
+        local_dest = (long long)n + P.nodes_per_grp;
+        if (local_dest >= P.num_nodes) local_dest -= P.num_nodes;
     } else if (P.traffic == DFD_TR_NEAREST_NEIGHBOR) {
-        local_dest = ((long long)n + 1) % P.num_nodes;
+        local_dest = (long long)n + 1;
+        if (local_dest >= P.num_nodes) local_dest -= P.num_nodes;
     } else if (P.traffic == DFD_TR_RAND_PERM) {
         if (s->dest_id == -1 || s->rperm_data > P.rperm_threshold) {
             s->dest_id = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.num_nodes - 1, &s->rng_draws);
@@ -253,7 +277,7 @@ __device__ void svr_kickoff(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doub
             s->rperm_data += P.payload_sz;
         }
     } else {  // RANDOM_OTHER_GROUP synthetic:375-392
-        int my_group_id = n / P.nodes_per_grp;
+        int my_group_id = (int)s->grp;
         int sel = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.G - 2, &s->rng_draws);
         int rand_group = sel >= my_group_id ? sel + 1 : sel;
         int rand_node = (int)clcg4_integer(s->rng_svr0, 0, (long long)P.nodes_per_grp - 1, &s->rng_draws);
@@ -262,7 +286,7 @@ __device__ void svr_kickoff(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doub
     if (now >= P.warm_up_time) s->warm_msg_sent_count++;
     s->msg_sent_count++;
     s->last_send_ts = now;
-    unsigned my_svr = svr_gid(P, n);
+    unsigned my_svr = s->svr_gid;
     // model_net_event(net_id, "test", global_dest, PAYLOAD_SZ, 0.0, remote, local, lp)
     if ((unsigned)local_dest == n && P.payload_sz < P.node_eager_limit && !P.noop_bypass) {
         // model_net_noop_event model-net.c:252-286 (same terminal on both ends)
@@ -296,7 +320,7 @@ __device__ void svr_remote(Ctx& c, unsigned n, NodeState* s, double now, unsigne
             atomicAdd(&A.ack_count[src_svr], 1u);
             atomicMin(&A.ack_first[src_svr], d2bits(now));
             atomicMax(&A.ack_last[src_svr], d2bits(now));
-            c.ev[EV_ACK]++;
+            COUNT_EV(c, EV_ACK);
         }
     }
 }
@@ -316,7 +340,7 @@ __device__ int mn_fcfs_next(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doub
         psize = P.mn_packet_size;
         is_last_packet = 0;
     }
-    node_add_event(c, n, s, list, now + 0.0, term_gid(P, n), s->term_seq++, EV_T_GENERATE | (is_last_packet ? NEV_FLAG_LAST : 0), q->dst_svr,
+    node_add_event(c, n, s, list, now + 0.0, s->term_gid, s->term_seq++, EV_T_GENERATE | (is_last_packet ? NEV_FLAG_LAST : 0), q->dst_svr,
                    q->msg_size, psize, q->msg_start_time, q->msg_id);
     if (is_last_packet) {
         s->sq_head++;
@@ -342,7 +366,7 @@ __device__ void mn_new_msg(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doubl
         double exp_time = (s->next_available_time > now) ? s->next_available_time : now;
         exp_time += P.nic_seq_delay + node_cll(P, s, s->rng_term2);
         s->next_available_time = exp_time;
-        node_add_event(c, n, s, list, now + (exp_time - now), term_gid(P, n), s->term_seq++, EV_NEW_MSG, ev.a, ev.b, 0, ev.d);
+        node_add_event(c, n, s, list, now + (exp_time - now), s->term_gid, s->term_seq++, EV_NEW_MSG, ev.a, ev.b, 0, ev.d);
         return;
     }
     if (s->sq_count >= (unsigned)P.nsq_cap) {
@@ -363,7 +387,7 @@ __device__ void mn_new_msg(Ctx& c, unsigned n, NodeState* s, NodeEv* list, doubl
     }
 }
 
-__device__ __forceinline__ unsigned num_chunks_for(unsigned sz, unsigned chunk) { return sz ? (sz + chunk - 1) / chunk : 1; }  // dally:103-104
+__device__ __forceinline__ unsigned num_chunks_for(unsigned sz, unsigned chunk) { return sz <= chunk ? 1u : (sz + chunk - 1) / chunk; }  // dally:103-104
 
 // packet_generate dally:5417-5774
 __device__ void term_packet_generate(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const NodeEv& ev) {
@@ -374,10 +398,10 @@ __device__ void term_packet_generate(Ctx& c, unsigned n, NodeState* s, NodeEv* l
     s->packet_gen++;
     s->total_gen_size += packet_size;
     unsigned nchunks = num_chunks_for(packet_size, P.chunk_size);
-    int my_router = n / P.p;
-    int dest_router_id = dst_term / P.p;
-    int dest_grp_id = dest_router_id / P.a;
-    int src_grp_id = my_router / P.a;
+    int my_router = (int)s->router;
+    int dest_router_id = (int)fastdiv(dst_term, P.magic_p);
+    int dest_grp_id = (int)fastdiv((unsigned)dest_router_id, P.magic_a);
+    int src_grp_id = (int)s->grp;
     if (src_grp_id == dest_grp_id) {
         if (dest_router_id == my_router)
             s->local_sr++;
@@ -399,15 +423,16 @@ __device__ void term_packet_generate(Ctx& c, unsigned n, NodeState* s, NodeEv* l
         t->total_size = total_size;
         t->message_id = message_id;
         t->chunk_id = i;
-        t->flags = flags;
+        t->flags = flags | ((unsigned)dest_grp_id << 16);
+        t->dst_router = (unsigned)dest_router_id;
         t->msg_start_time = ev.d;
         s->tq_count++;
         s->terminal_length += P.chunk_size;
     }
     if (s->tq_count > s->tq_hwm) s->tq_hwm = s->tq_count;
-    double injection_ts = bytes_to_ns(packet_size, P.cn_bw);
+    double injection_ts = packet_size == (unsigned)P.payload_sz ? P.inj_packet_cn : bytes_to_ns(packet_size, P.cn_bw);
     double nic_ts = injection_ts;
-    unsigned tg = term_gid(P, n);
+    unsigned tg = s->term_gid;
     if (s->terminal_length < P.cn_vc) {
         node_add_event(c, n, s, list, now + nic_ts, tg, s->term_seq++, EV_SCHED_NEXT);  // model_net_method_idle_event2
     } else {
@@ -422,7 +447,7 @@ __device__ void term_packet_generate(Ctx& c, unsigned n, NodeState* s, NodeEv* l
     s->stats_used = 1;
     s->send_count++;
     s->send_bytes += packet_size;
-    s->send_time += (1 / P.cn_bw) * packet_size;
+    s->send_time += P.inv_cn_bw * packet_size;
     if (s->max_event_size < total_event_size) s->max_event_size = total_event_size;
 }
 
@@ -438,17 +463,17 @@ __device__ void term_packet_send(Ctx& c, unsigned n, NodeState* s, NodeEv* list,
     }
     TermChunk cur = A.tq[(size_t)n * P.ntq_cap + (s->tq_head & (P.ntq_cap - 1))];
     unsigned nchunks = num_chunks_for(cur.packet_size, P.chunk_size);
-    double injection_delay = bytes_to_ns(P.chunk_size, P.cn_bw);
+    double injection_delay = P.inj_chunk_cn;
     if ((cur.packet_size < (unsigned)P.chunk_size) && (cur.chunk_id == nchunks - 1)) {
-        unsigned data_size = cur.packet_size % P.chunk_size;
-        injection_delay = bytes_to_ns(data_size, P.cn_bw);
+        unsigned data_size = mod_chunk(cur.packet_size, P.chunk_size);
+        injection_delay = inj_delay(P, data_size, BW_CN);
     }
     double propagation_delay = P.cn_delay;
     s->terminal_available_time = maxd(s->terminal_available_time, now);
     s->terminal_available_time += injection_delay;
     double injection_ts = s->terminal_available_time - now;
     double propagation_ts = injection_ts + propagation_delay;
-    unsigned tg = term_gid(P, n);
+    unsigned tg = s->term_gid;
     {
         ChunkRec rec;
         rec.ts = now + propagation_ts;
@@ -460,8 +485,10 @@ __device__ void term_packet_send(Ctx& c, unsigned n, NodeState* s, NodeEv* list,
         rec.message_id = cur.message_id;
         rec.packet_size = cur.packet_size;
         rec.total_size = cur.total_size;
-        rec.chunk_id = cur.chunk_id;
+        rec.chunk_id = (uint16_t)cur.chunk_id;
+        rec.dst_grp = (uint16_t)(cur.flags >> 16);
         rec.intm_grp_id = -1;
+        rec.org_grp = (uint16_t)s->grp;
         rec.prev_lp = n;
         rec.prev_port = 0;  // vc_index = vcg = 0
         rec.prev_vc = 0;    // output_chan = vcg
@@ -473,11 +500,11 @@ __device__ void term_packet_send(Ctx& c, unsigned n, NodeState* s, NodeEv* list,
         rec.pad0 = 0;
         rec.travel_start_time = now;
         rec.msg_start_time = cur.msg_start_time;
-        rec.origin_router = n / P.p;
+        rec.origin_router = s->router;
         rec.src_svr = n;
         rec.dst_svr = cur.dst_svr;
-        rec.pad1 = 0;
-        push_chunk_to_router(c, n / P.p, rec);
+        rec.dst_router = cur.dst_router;
+        push_chunk_to_router(c, s->router, rec);
     }
     if (cur.chunk_id == nchunks - 1 && (cur.flags & 2u)) {  // LOCAL completion event to the sender svr at +0
         node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_LOCAL);
@@ -509,7 +536,7 @@ __device__ __forceinline__ void term_buf_update(Ctx& c, unsigned n, NodeState* s
     const DfdParams& P = *c.P;
     s->vc_occupancy -= P.chunk_size;
     if (s->in_send_loop == 0 && s->tq_count != 0) {
-        node_add_event(c, n, s, list, now + 0.0, term_gid(P, n), s->term_seq++, EV_T_SEND);
+        node_add_event(c, n, s, list, now + 0.0, s->term_gid, s->term_seq++, EV_T_SEND);
         s->in_send_loop = 1;
     }
 }
@@ -523,7 +550,7 @@ __device__ void term_packet_arrive(Ctx& c, unsigned n, NodeState* s, NodeEv* lis
         set_error(A, DFD_ERR_WRONG_TERMINAL, n);
         return;
     }
-    unsigned tg = term_gid(P, n);
+    unsigned tg = s->term_gid;
     push_credit_to_router(c, m.prev_lp, now + P.cn_credit, tg, s->term_seq++, m.prev_port, m.prev_vc);
     s->finished_chunks++;
     s->ejected_chunks++;
@@ -553,10 +580,19 @@ __device__ void term_packet_arrive(Ctx& c, unsigned n, NodeState* s, NodeEv* lis
 __device__ void node_process(Ctx& c, unsigned n) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
+#ifdef DFD_PROFILE
+    long long prof_lp0 = clock64();
+#endif
     NodeState* s = &A.node[n];
     NodeEv* list = &A.nev[(size_t)n * P.nev_cap];
     const unsigned cmask = P.ncin_cap - 1, kmask = P.nkin_cap - 1;
     double next_ts;
+    // heads of the two single-producer rings: read once, re-read only after a pop (a record written during
+    // this window is not due before the next one)
+    ChunkRec* ch = &A.ncin[(size_t)n * P.ncin_cap + (s->cin_head & cmask)];
+    CreditRec* kr = &A.nkin[(size_t)n * P.nkin_cap + (s->kin_head & kmask)];
+    int4 chh = __ldcg((const int4*)ch);
+    int4 krh = __ldcg((const int4*)kr);
     for (;;) {
         // earliest self event
         int bi = -1;
@@ -572,8 +608,6 @@ __device__ void node_process(Ctx& c, unsigned n) {
                 bseq = e.seq;
             }
         }
-        ChunkRec* ch = &A.ncin[(size_t)n * P.ncin_cap + (s->cin_head & cmask)];
-        int4 chh = __ldcg((const int4*)ch);
         double cts = __longlong_as_double(((long long)(unsigned)chh.y << 32) | (unsigned)chh.x);
         if (d2bits(cts) != INF_BITS && (bts == DINF || key_less(cts, (unsigned)chh.z, (unsigned)chh.w, bts, bsrc, bseq))) {
             kind = 1;
@@ -581,8 +615,6 @@ __device__ void node_process(Ctx& c, unsigned n) {
             bsrc = (unsigned)chh.z;
             bseq = (unsigned)chh.w;
         }
-        CreditRec* kr = &A.nkin[(size_t)n * P.nkin_cap + (s->kin_head & kmask)];
-        int4 krh = __ldcg((const int4*)kr);
         double kts = __longlong_as_double(((long long)(unsigned)krh.y << 32) | (unsigned)krh.x);
         if (d2bits(kts) != INF_BITS && (bts == DINF || key_less(kts, (unsigned)krh.z, (unsigned)krh.w, bts, bsrc, bseq))) {
             kind = 2;
@@ -596,6 +628,7 @@ __device__ void node_process(Ctx& c, unsigned n) {
         }
         double now = bts;
         s->events++;
+        PROF_T0();
         if (kind == 1) {
             ChunkRec m;
             int4* dst = (int4*)&m;
@@ -604,19 +637,25 @@ __device__ void node_process(Ctx& c, unsigned n) {
             for (int i = 1; i < 6; i++) dst[i] = __ldcg((const int4*)ch + i);
             __stcg((unsigned long long*)&ch->ts, INF_BITS);
             s->cin_head++;
-            c.ev[EV_T_ARRIVE]++;
+            ch = &A.ncin[(size_t)n * P.ncin_cap + (s->cin_head & cmask)];
+            chh = __ldcg((const int4*)ch);
+            COUNT_EV(c, EV_T_ARRIVE);
             term_packet_arrive(c, n, s, list, now, m);
+            PROF_ADD(c, EV_T_ARRIVE);
         } else if (kind == 2) {
             __stcg((unsigned long long*)&kr->ts, INF_BITS);
             s->kin_head++;
-            c.ev[EV_T_BUFFER]++;
+            kr = &A.nkin[(size_t)n * P.nkin_cap + (s->kin_head & kmask)];
+            krh = __ldcg((const int4*)kr);
+            COUNT_EV(c, EV_T_BUFFER);
             term_buf_update(c, n, s, list, now);
+            PROF_ADD(c, EV_T_BUFFER);
         } else {
             NodeEv ev = list[bi];
             list[bi] = list[s->nev - 1];
             s->nev--;
             unsigned type = ev.type & 0xFF;
-            c.ev[type]++;
+            COUNT_EV(c, type);
             switch (type) {
             case EV_KICKOFF: svr_kickoff(c, n, s, list, now); break;
             case EV_REMOTE: svr_remote(c, n, s, now, ev.a, ev.d); break;
@@ -629,10 +668,15 @@ __device__ void node_process(Ctx& c, unsigned n) {
             case EV_T_SEND: term_packet_send(c, n, s, list, now); break;
             default: break;
             }
+            PROF_ADD(c, type);
         }
     }
     A.wake_self[n] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
+#ifdef DFD_PROFILE
+    atomicAdd(&A.counters[48], (unsigned long long)(clock64() - prof_lp0));
+    atomicAdd(&A.counters[49], 1ULL);
+#endif
 }
 
 // ================================================================================================
@@ -748,9 +792,8 @@ __device__ int cand_port(const DfdParams& P, const DfdArrays& A, const RCtx& R, 
     return -1;
 }
 // get_legal_minimal_stops dally:9793-9849
-__device__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, const RCtx& R, int fdest_router) {
+__device__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, const RCtx& R, int fdest_router, int fg) {
     Cands cd;
-    int fg = fdest_router / P.a;
     if (R.grp != fg) {
         grp_range(P, A, R.r, fg, &cd.lo, &cd.hi);
         if (cd.hi > cd.lo) {
@@ -765,7 +808,7 @@ __device__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, con
         return cd;
     }
     int lo, hi;
-    loc_range(P, A, R.lid, fdest_router % P.a, &lo, &hi);
+    loc_range(P, A, R.lid, fdest_router - fg * P.a, &lo, &hi);
     cd.kind = 3;
     cd.lo = lo;
     cd.hi = hi;
@@ -828,16 +871,16 @@ __device__ int best_from_k2(const DfdParams& P, const DfdArrays& A, RCtx& R, con
 }
 
 // dfdally_select_intermediate_group dally:9738-9790
-__device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m, int fdest_router) {
-    int fg = fdest_router / P.a;
-    int og = m.origin_router / P.a;
+__device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
+    int fg = m.dst_grp;
+    int og = m.org_grp;
     if (m.intm_grp_id == -1) {
         int sel = (int)r_integer(R, 0, (long long)P.G - 3);  // groups other than origin and destination, ascending
         int lo = og < fg ? og : fg, hi = og < fg ? fg : og;
         int g = sel;
         if (g >= lo) g++;
         if (g >= hi) g++;
-        m.intm_grp_id = g;
+        m.intm_grp_id = (int16_t)g;
     } else {
         // re-pick among the groups this router links to directly (set<int>: ascending, unique)
         const int* gg = A.gs_group + (size_t)R.r * P.h;
@@ -853,7 +896,7 @@ __device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A
             int g = gg[i];
             if (g != prev && g != fg && g != og) {
                 if (sel == 0) {
-                    m.intm_grp_id = g;
+                    m.intm_grp_id = (int16_t)g;
                     break;
                 }
                 sel--;
@@ -864,11 +907,11 @@ __device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A
 }
 
 // get_legal_nonminimal_stops dally:9853-9910
-__device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m, int fdest_router) {
+__device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
     Cands cd;
     cd.kind = 0;
     cd.lo = cd.hi = cd.n = 0;
-    int og = m.origin_router / P.a;
+    int og = m.org_grp;
     if (R.grp == og) {
         grp_range(P, A, R.r, m.intm_grp_id, &cd.lo, &cd.hi);
         if (cd.hi > cd.lo) {
@@ -882,7 +925,7 @@ __device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, 
             cd.n = routed_count(P, A, R, m.intm_grp_id);
             return cd;
         }
-        select_intermediate_group(P, A, R, m, fdest_router);
+        select_intermediate_group(P, A, R, m);
         grp_range(P, A, R.r, m.intm_grp_id, &cd.lo, &cd.hi);
         cd.kind = 1;
         cd.n = cd.hi - cd.lo;
@@ -895,12 +938,12 @@ __device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, 
 __device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
-    int fg = fdest_router / P.a;
+    int fg = m.dst_grp;
     if ((int)R.r == fdest_router) {  // destination router: the terminal port (one rail -> no draw)
-        return P.intra_radix + P.global_radix + (int)(m.dst_term % P.p);
+        return P.intra_radix + P.global_radix + (int)(m.dst_term - (unsigned)fdest_router * P.p);
     } else if (R.grp == fg) {  // destination group: local link(s) to the destination router
         Cands cd;
-        loc_range(P, A, R.lid, fdest_router % P.a, &cd.lo, &cd.hi);
+        loc_range(P, A, R.lid, fdest_router - fg * P.a, &cd.lo, &cd.hi);
         cd.kind = 3;
         cd.n = cd.hi - cd.lo;
         if (cd.n < 1) {
@@ -910,9 +953,9 @@ __device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
         if (P.routing == DFD_PROG_ADAPTIVE) return best_from_cands(P, A, R, cd);
         return cand_port(P, A, R, cd, (int)r_integer(R, 0, cd.n - 1));
     }
-    if (m.last_hop == DFD_HOP_TERMINAL && m.intm_grp_id == -1) select_intermediate_group(P, A, R, m, fdest_router);
+    if (m.last_hop == DFD_HOP_TERMINAL && m.intm_grp_id == -1) select_intermediate_group(P, A, R, m);
     if (P.routing == DFD_MINIMAL) {  // dfdally_minimal_routing dally:9913-9932
-        Cands cd = legal_minimal_stops(P, A, R, fdest_router);
+        Cands cd = legal_minimal_stops(P, A, R, fdest_router, fg);
         if (cd.n < 1) {
             set_error(A, DFD_ERR_DEAD_END, R.r);
             return -1;
@@ -941,8 +984,8 @@ __device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
     }
     // dfdally_prog_adaptive_routing dally:9995-10061
     if (R.grp == m.intm_grp_id) m.is_intm_visited = 1;
-    Cands mins = legal_minimal_stops(P, A, R, fdest_router);
-    Cands nonmins = legal_nonminimal_stops(P, A, R, m, fdest_router);
+    Cands mins = legal_minimal_stops(P, A, R, fdest_router, fg);
+    Cands nonmins = legal_nonminimal_stops(P, A, R, m);
     int best_min, best_non;
     if (mins.n > 0 && mins.kind == 1)
         best_min = best_from_k2(P, A, R, mins);
@@ -993,7 +1036,7 @@ __device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     PoolSlot& m = R.pool[slot];
-    int dest_router_id = m.dst_term / P.p;
+    int dest_router_id = (int)m.dst_router;
     int in_path_type = m.path_type;  // msg->path_type (as received)
     unsigned in_port = m.prev_port, in_vc = m.prev_vc, in_last_hop = m.last_hop, in_prev = m.prev_lp;
     if (m.last_hop == DFD_HOP_TERMINAL) m.path_type = DFD_MINIMAL;
@@ -1017,8 +1060,8 @@ __device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot
     }
     m.out_port = (uint16_t)output_port;
     int max_vc_size = P.cn_vc;
-    int src_group_id = m.origin_router / P.a;
-    int dest_group_id = dest_router_id / P.a;
+    int src_group_id = m.org_grp;
+    int dest_group_id = m.dst_grp;
     int output_chan = 0;
     if (R.grp == src_group_id) {
         output_chan = m.l_hop;
@@ -1092,25 +1135,24 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
         ps.busy_time += (now - ps.last_buf_full);
         ps.last_buf_full = 0.0;
     }
-    int to_terminal = 1, global = 0;
+    int to_terminal = 1, global = 0, bw = BW_CN;
     double delay = P.cn_delay;
-    double bandwidth = P.cn_bw;
     if (output_port < P.intra_radix) {
         to_terminal = 0;
         delay = P.local_delay;
-        bandwidth = P.local_bw;
+        bw = BW_LOCAL;
     } else if (output_port < P.intra_radix + P.num_global_channels) {
         to_terminal = 0;
         global = 1;
         delay = P.global_delay;
-        bandwidth = P.global_bw;
+        bw = BW_GLOBAL;
     }
     unsigned nchunks = num_chunks_for(m.packet_size, P.chunk_size);
+    unsigned tail = mod_chunk(m.packet_size, P.chunk_size);
     double propagation_delay = delay;
-    double injection_delay = bytes_to_ns(P.chunk_size, bandwidth);
-    if (m.packet_size == 0) injection_delay = bytes_to_ns(P.credit_size, bandwidth);
-    if ((m.packet_size < (unsigned)P.chunk_size) && (m.chunk_id == nchunks - 1))
-        injection_delay = bytes_to_ns(m.packet_size % P.chunk_size, bandwidth);
+    double injection_delay = inj_delay(P, P.chunk_size, bw);
+    if (m.packet_size == 0) injection_delay = inj_delay(P, P.credit_size, bw);
+    if ((m.packet_size < (unsigned)P.chunk_size) && (m.chunk_id == nchunks - 1)) injection_delay = inj_delay(P, tail, bw);
     injection_delay += P.router_delay;
     ps.noat = maxd(ps.noat, now);
     ps.noat += injection_delay;
@@ -1128,7 +1170,9 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
         rec.packet_size = m.packet_size;
         rec.total_size = m.total_size;
         rec.chunk_id = m.chunk_id;
+        rec.dst_grp = m.dst_grp;
         rec.intm_grp_id = m.intm_grp_id;
+        rec.org_grp = m.org_grp;
         rec.prev_lp = R.r;  // intm_lp_id
         rec.prev_port = m.out_port;
         rec.prev_vc = m.out_vc;
@@ -1146,14 +1190,14 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
         rec.origin_router = m.origin_router;
         rec.src_svr = m.src_svr;
         rec.dst_svr = m.dst_svr;
-        rec.pad1 = 0;
+        rec.dst_router = m.dst_router;
         if (to_terminal)
             push_chunk_to_node(c, m.next_stop, rec);
         else
             push_chunk_to_router(c, m.next_stop, rec);
     }
-    if (((m.packet_size % P.chunk_size) || m.packet_size == 0) && (m.chunk_id == nchunks - 1))
-        ps.link_traffic += (m.packet_size % P.chunk_size);
+    if ((tail || m.packet_size == 0) && (m.chunk_id == nchunks - 1))
+        ps.link_traffic += tail;
     else
         ps.link_traffic += P.chunk_size;
     ps.total_chunks++;
@@ -1204,12 +1248,15 @@ __device__ void router_buf_update(Ctx& c, RCtx& R, double now, int indx, int out
 __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned ntail_k) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
+#ifdef DFD_PROFILE
+    long long prof_lp0 = clock64();
+#endif
     RCtx R;
     R.r = r;
-    R.gid = rtr_gid(P, r);
-    R.lid = r % P.a;
-    R.grp = r / P.a;
     R.h = &A.rh[r];
+    R.gid = R.h->gid;
+    R.lid = R.h->lid;
+    R.grp = R.h->grp;
     R.port = &A.port[(size_t)r * P.radix];
     R.pq = &A.portq[(size_t)r * P.radix];
     R.pool = &A.pool[(size_t)r * P.rpool_cap];
@@ -1251,39 +1298,78 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
         double now = e.ts;
         R.h->events++;
         unsigned kind = e.ref >> 28;
+        PROF_T0();
         if (kind == RK_CHUNK) {
-            c.ev[EV_R_ARRIVE]++;
+            COUNT_EV(c, EV_R_ARRIVE);
             router_packet_receive(c, R, now, e.ref & 0x0FFFFFFFu);
+            PROF_ADD(c, EV_R_ARRIVE);
         } else if (kind == RK_CREDIT) {
-            c.ev[EV_R_BUFFER]++;
+            COUNT_EV(c, EV_R_BUFFER);
             router_buf_update(c, R, now, e.ref & 0xFFFFu, (e.ref >> 16) & 0xFFu);
+            PROF_ADD(c, EV_R_BUFFER);
         } else {
-            c.ev[EV_R_SEND]++;
+            COUNT_EV(c, EV_R_SEND);
             router_packet_send(c, R, now, e.ref & 0xFFFFu);
+            PROF_ADD(c, EV_R_SEND);
         }
     }
     double next_ts = R.h->heap_n ? R.heap[0].ts : DINF;
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
+#ifdef DFD_PROFILE
+    atomicAdd(&A.counters[50], (unsigned long long)(clock64() - prof_lp0));
+    atomicAdd(&A.counters[51], 1ULL);
+    if (ntail_c | ntail_k) atomicAdd(&A.counters[52], 1ULL);
+#endif
 }
 
 // ================================================================================================
 // the window loop
 // ================================================================================================
+// Grid barrier that keeps L1 valid: the arrival is a release (MEMBAR.ALL.GPU + RED, no CCTL.IVALL), the wait
+// is a relaxed poll.  Everything another LP may have written is read with ld.cg (L2), so no acquire -- and
+// therefore no L1 invalidation -- is needed; LP-private state stays L1-resident across windows because an LP
+// is always processed by the same block.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ULL) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+// Each block owns a contiguous slice of the nodes and of the routers.  Per window: (1) a coalesced scan of the
+// slice's wake words compacts the LPs that have work into a shared-memory list, (2) the list is dealt out
+// warp-first (lane 0 of every warp, then lane 1, ...) so that concurrently active LPs do not serialise inside
+// one warp, (3) block-min of the next timestamps -> one atomicMin, (4) grid barrier.
 __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, unsigned long long max_windows) {
-    cg::grid_group grid = cg::this_grid();
+    extern __shared__ unsigned s_list[];  // [lps_per_block]: bit31 = router, low bits = index; then tc/tk halves
     __shared__ double s_min[DFD_BLOCK / 32];
-    __shared__ unsigned long long s_ev[EV_NTYPES];
-    const unsigned nthreads = gridDim.x * blockDim.x;
-    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned ttid = threadIdx.x * gridDim.x + blockIdx.x;  // transposed: spreads routers over all blocks
+    __shared__ unsigned s_ev[EV_NTYPES];
+    __shared__ unsigned s_n;
+    const unsigned tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
+    const unsigned ntb = (P.NT + gridDim.x - 1) / gridDim.x, nrb = (P.NR + gridDim.x - 1) / gridDim.x;
+    const unsigned n0 = min((unsigned)P.NT, blockIdx.x * ntb), n1 = min((unsigned)P.NT, n0 + ntb);
+    const unsigned r0 = min((unsigned)P.NR, blockIdx.x * nrb), r1 = min((unsigned)P.NR, r0 + nrb);
+    unsigned* s_tails = s_list + (ntb + nrb);
     Ctx c;
     c.P = &P;
     c.A = &A;
-    for (int i = 0; i < EV_NTYPES; i++) c.ev[i] = 0;
-    unsigned long long w = A.counters[1];  // windows executed so far (the kernel may be re-entered)
-    unsigned long long w_stop = w + max_windows;
+    c.ev = s_ev;
+    if (tid < EV_NTYPES) s_ev[tid] = 0;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    unsigned long long w = __ldcg(&A.counters[1]);  // windows executed so far (the kernel may be re-entered)
+    const unsigned long long w_stop = w + max_windows;
+    const unsigned long long bar0 = __ldcg(&A.counters[28]);  // barrier count at entry
+    unsigned long long nbar = 0;
+    long long t_scan = 0, t_proc = 0, t_bar = 0, t_procmax = 0;  // cycle accounting (thread 0 of each block)
     for (;;) {
+        long long c0 = clock64();
         unsigned long long tb = __ldcg(&A.gmin[w % 3]);
         if (tb >= INF_BITS || __ldcg(&A.counters[2]) != 0 || w >= w_stop) break;
         double T = bits2d(tb);
@@ -1292,56 +1378,85 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
         c.cur = (int)(w & 1);
         c.nxt = c.cur ^ 1;
         c.cand = DINF;
-        if (gtid == 0) A.gmin[(w + 2) % 3] = INF_BITS;
-        unsigned long long te_bits = d2bits(c.t_end);
-        for (unsigned n = gtid; n < (unsigned)P.NT; n += nthreads) {
+        if (blockIdx.x == 0 && tid == 0) __stcg(&A.gmin[(w + 2) % 3], INF_BITS);
+        const unsigned long long te_bits = d2bits(c.t_end);
+        // (1) scan + compact
+        for (unsigned n = n0 + tid; n < n1; n += nth) {
             unsigned long long ws = A.wake_self[n];
             unsigned long long wi = __ldcg(&A.wake_in[(size_t)c.cur * P.NT + n]);
             if (wi != INF_BITS) {
-                A.wake_in[(size_t)c.cur * P.NT + n] = INF_BITS;
+                __stcg(&A.wake_in[(size_t)c.cur * P.NT + n], INF_BITS);
                 if (wi < ws) {
                     ws = wi;
                     A.wake_self[n] = ws;
                 }
             }
             if (ws < te_bits)
-                node_process(c, n);
+                s_list[atomicAdd(&s_n, 1u)] = n;
             else
                 c.cand = fmin(c.cand, bits2d(ws));
         }
-        for (unsigned r = ttid; r < (unsigned)P.NR; r += nthreads) {
+        for (unsigned r = r0 + tid; r < r1; r += nth) {
             unsigned long long ws = A.wake_self[P.NT + r];
             unsigned tc = __ldcg(&A.rcin_tail[(size_t)c.cur * P.NR + r]);
             unsigned tk = __ldcg(&A.rkin_tail[(size_t)c.cur * P.NR + r]);
-            if (tc | tk | (unsigned)(ws < te_bits))
-                router_process(c, r, tc, tk);
-            else
+            if (tc | tk | (unsigned)(ws < te_bits)) {
+                unsigned pos = atomicAdd(&s_n, 1u);
+                s_list[pos] = 0x80000000u | r;
+                s_tails[pos] = (tc << 16) | (tk & 0xFFFFu);
+            } else
                 c.cand = fmin(c.cand, bits2d(ws));
         }
-        // block-min of the candidates, one atomicMin per block, then the grid barrier that closes the window
+        __syncthreads();
+        long long c1 = clock64();
+        // (2) process, warp-first distribution
+        const unsigned nact = s_n;
+        for (unsigned j = (tid & 31) * nwarps + (tid >> 5); j < nact; j += nth) {
+            unsigned e = s_list[j];
+            if (e & 0x80000000u) {
+                unsigned t = s_tails[j];
+                router_process(c, e & 0x7FFFFFFFu, t >> 16, t & 0xFFFFu);
+            } else
+                node_process(c, e);
+        }
+        // (3) block-min of the candidates, one atomicMin per block
         double v = c.cand;
         for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = v;
+        if ((tid & 31) == 0) s_min[tid >> 5] = v;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             double m = s_min[0];
-            for (int i = 1; i < DFD_BLOCK / 32; i++) m = fmin(m, s_min[i]);
+            for (unsigned i = 1; i < nwarps; i++) m = fmin(m, s_min[i]);
             if (d2bits(m) != INF_BITS) atomicMin(&A.gmin[(w + 1) % 3], d2bits(m));
+            s_n = 0;
         }
-        grid.sync();
+        // (4) close the window
+        long long c2 = clock64();
+        nbar++;
+        grid_barrier(&A.counters[29], (bar0 + nbar) * gridDim.x);
+        long long c3 = clock64();
+        t_scan += c1 - c0;
+        t_proc += c2 - c1;
+        t_bar += c3 - c2;
+        if (c2 - c1 > t_procmax) t_procmax = c2 - c1;
         w++;
     }
-    // fold the per-thread event counters
-    if (threadIdx.x < EV_NTYPES) s_ev[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = 0; i < EV_NTYPES; i++)
-        if (c.ev[i]) atomicAdd(&s_ev[i], c.ev[i]);
-    __syncthreads();
-    if (threadIdx.x < EV_NTYPES && s_ev[threadIdx.x]) {
-        atomicAdd(&A.counters[4 + threadIdx.x], s_ev[threadIdx.x]);
-        atomicAdd(&A.counters[0], s_ev[threadIdx.x]);
+    if (tid < EV_NTYPES && s_ev[tid]) {
+        atomicAdd(&A.counters[4 + tid], (unsigned long long)s_ev[tid]);
+        atomicAdd(&A.counters[0], (unsigned long long)s_ev[tid]);
     }
-    if (gtid == 0) A.counters[1] = w;
+    if (tid == 0) {  // per-block cycle sums: scan / process / barrier wait
+        atomicAdd(&A.counters[20], (unsigned long long)t_scan);
+        atomicAdd(&A.counters[21], (unsigned long long)t_proc);
+        atomicAdd(&A.counters[22], (unsigned long long)t_bar);
+        atomicMax(&A.counters[23], (unsigned long long)t_proc);
+        atomicMax(&A.counters[24], (unsigned long long)t_procmax);
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        A.counters[1] = w;
+        A.counters[28] = bar0 + nbar;
+    }
 }
 
 // ================================================================================================
@@ -1367,7 +1482,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         A.gmin[0] = d2bits(P.mean_interval);
         A.gmin[1] = INF_BITS;
         A.gmin[2] = INF_BITS;
-        for (int i = 0; i < 4 + EV_NTYPES; i++) A.counters[i] = 0;
+        for (int i = 0; i < 64; i++) A.counters[i] = 0;
     }
     for (unsigned n = gtid; n < (unsigned)P.NT; n += nthreads) {
         NodeState* s = &A.node[n];
@@ -1377,6 +1492,10 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         seed_stream(s->rng_svr2, (unsigned long long)sg * 3 + 2, K);
         seed_stream(s->rng_term2, (unsigned long long)tg * 3 + 2, K);
         s->dest_id = -1;
+        s->svr_gid = sg;
+        s->term_gid = tg;
+        s->router = n / P.p;
+        s->grp = s->router / P.a;
         s->min_latency = 2147483647.0;  // INT_MAX dally:4766
         // svr_init synthetic:287-298: first KICKOFF at mean_interval
         NodeEv* ev = &A.nev[(size_t)n * P.nev_cap];
@@ -1402,6 +1521,9 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         memset(h, 0, sizeof(RouterHdr));
         seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
         h->pool_free = 0;
+        h->gid = rtr_gid(P, r);
+        h->lid = (uint16_t)(r % P.a);
+        h->grp = (uint16_t)(r / P.a);
         A.wake_self[P.NT + r] = INF_BITS;
         A.rcin_tail[r] = 0;
         A.rcin_tail[(size_t)P.NR + r] = 0;
@@ -1483,7 +1605,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     if (dalloc(dev, &A.rkin, 2 * NR * P.rkin_cap)) return 1;
     if (dalloc(dev, &A.rcin_tail, 2 * NR)) return 1;
     if (dalloc(dev, &A.rkin_tail, 2 * NR)) return 1;
-    if (dalloc(dev, &A.counters, 32)) return 1;
+    if (dalloc(dev, &A.counters, 64)) return 1;
     int *loc_off, *loc_port, *loc_dest, *gs_port, *gs_group, *gdest, *routed_off, *routed_lid;
     if (dalloc(dev, &loc_off, T.loc_off.size())) return 1;
     if (dalloc(dev, &loc_port, T.loc_port.size())) return 1;
@@ -1502,17 +1624,36 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     A.routed_off = routed_off;
     A.routed_lid = routed_lid;
     dev->topo_bytes = 0;
-    // grid: persistent, co-resident (cooperative launch)
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfd_run_kernel, DFD_BLOCK, 0));
-    if (per_sm < 1) {
-        snprintf(dev->error, sizeof dev->error, "run kernel does not fit on an SM");
-        return 1;
+    // grid: persistent and co-resident (cooperative launch).  The engine is latency-bound (one grid barrier per
+    // lookahead window), so LPs are spread thinly: ~DFD_LPS_PER_BLOCK LPs per block until every SM holds
+    // blocks_per_sm blocks, after which the per-block slice grows.
+    dev->block = DFD_BLOCK;
+    if (const char* ev = getenv("DFD_BLOCK_THREADS")) dev->block = std::max(32, std::min(DFD_BLOCK, atoi(ev) / 32 * 32));
+    int lps_per_block = 16;
+    if (const char* ev = getenv("DFD_LPS_PER_BLOCK")) lps_per_block = std::max(1, atoi(ev));
+    size_t want = (NLP + lps_per_block - 1) / lps_per_block;
+    for (int iter = 0; iter < 2; iter++) {
+        // dynamic shared memory depends on the slice size, which depends on the grid: settle in two passes
+        size_t g = iter == 0 ? want : (size_t)dev->grid;
+        size_t ntb = (NT + g - 1) / g, nrb = (NR + g - 1) / g;
+        dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
+        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfd_run_kernel, dev->block, dev->smem));
+        if (per_sm < 1) {
+            snprintf(dev->error, sizeof dev->error, "run kernel does not fit on an SM (%zu bytes of shared memory)", dev->smem);
+            return 1;
+        }
+        size_t maxb = (size_t)per_sm * dev->num_sms;
+        dev->grid = (int)std::max<size_t>(1, std::min(want, maxb));
+        dev->blocks_per_sm = per_sm;
     }
-    size_t want = (std::max(NT, NR) + DFD_BLOCK - 1) / DFD_BLOCK;
-    size_t maxb = (size_t)per_sm * dev->num_sms;
-    dev->grid = (int)std::max<size_t>(1, std::min(want, maxb));
-    dev->blocks_per_sm = per_sm;
+    if (const char* ev = getenv("DFD_GRID")) {
+        dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
+        size_t g = dev->grid, ntb = (NT + g - 1) / g, nrb = (NR + g - 1) / g;
+        dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
+        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
+    }
     return 0;
 }
 
@@ -1546,7 +1687,7 @@ int dfd_device_reset(DfdDevice* dev, cudaStream_t st) {
 
 int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windows) {
     void* args[] = {(void*)&dev->P, (void*)&dev->A, (void*)&max_windows};
-    CK(cudaLaunchCooperativeKernel((void*)dfd_run_kernel, dim3(dev->grid), dim3(DFD_BLOCK), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((void*)dfd_run_kernel, dim3(dev->grid), dim3(dev->block), args, dev->smem, st));
     return 0;
 }
 
@@ -1565,7 +1706,7 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st) {
     CK(cudaMemcpyAsync(out->ack_count.data(), A.ack_count, sizeof(unsigned) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->ack_first.data(), A.ack_first, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->ack_last.data(), A.ack_last, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     out->d2h_bytes = sizeof(NodeState) * (size_t)P.NT + sizeof(RouterHdr) * (size_t)P.NR + sizeof(PortState) * (size_t)P.NR * P.radix +
                      (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * (size_t)P.NT + sizeof(unsigned long long) * 32;

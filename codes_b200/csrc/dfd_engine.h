@@ -22,7 +22,7 @@ struct DfdHostResults {
     std::vector<PortState> port;
     std::vector<unsigned> ack_count;
     std::vector<unsigned long long> ack_first, ack_last;
-    unsigned long long counters[32];
+    unsigned long long counters[64];
     size_t d2h_bytes = 0;
 };
 
@@ -32,7 +32,8 @@ struct DfdDevice {
     DfdSeedConsts seeds;
     std::vector<void*> allocs;
     size_t bytes_allocated = 0, topo_bytes = 0;
-    int num_sms = 0, grid = 0, blocks_per_sm = 0;
+    int num_sms = 0, grid = 0, block = 0, blocks_per_sm = 0;
+    size_t smem = 0;
     char error[512] = {0};
 };
 

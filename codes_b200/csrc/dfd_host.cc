@@ -873,6 +873,20 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->nic_seq_delay = p.nic_seq_delay;
     P->lookahead = 0.005;  // g_tw_lookahead, ROSS default
     P->codes_cn_delay = 1 / p.mn_cn_bandwidth;
+    P->inj_chunk_cn = h_bytes_to_ns(p.chunk_size, p.cn_bandwidth);
+    P->inj_chunk_local = h_bytes_to_ns(p.chunk_size, p.local_bandwidth);
+    P->inj_chunk_global = h_bytes_to_ns(p.chunk_size, p.global_bandwidth);
+    {
+        unsigned tail = (unsigned)o.payload_sz % (unsigned)p.chunk_size;
+        P->inj_pay_cn = h_bytes_to_ns(tail, p.cn_bandwidth);
+        P->inj_pay_local = h_bytes_to_ns(tail, p.local_bandwidth);
+        P->inj_pay_global = h_bytes_to_ns(tail, p.global_bandwidth);
+    }
+    P->inj_packet_cn = h_bytes_to_ns(o.payload_sz, p.cn_bandwidth);
+    P->inv_cn_bw = 1 / p.cn_bandwidth;
+    P->magic_p = p.num_cn > 1 ? (~0ULL) / (unsigned long long)p.num_cn + 1 : 0;
+    P->magic_a = p.num_routers > 1 ? (~0ULL) / (unsigned long long)p.num_routers + 1 : 0;
+    if (p.num_groups > 32767 || p.total_routers > (1 << 30)) return fail(e, "topology too large for the packed chunk record");
     // lookahead window: the smallest delay of any event that crosses LPs (every chunk hop is at least
     // its link delay; every credit exactly its credit delay)
     double L = p.cn_delay;
@@ -1003,11 +1017,24 @@ int dfd_engine_finish(dfd_engine* e, void* stream) {
     S.d2h_bytes = e->res.d2h_bytes;
     S.device_bytes = e->dev.bytes_allocated;
     S.grid_blocks = e->dev.grid;
-    S.block_threads = 256;
+    S.block_threads = e->dev.block;
     S.num_sms = e->dev.num_sms;
     S.num_terminals = e->hp.total_terminals;
     S.num_routers = e->hp.total_routers;
     S.radix = e->hp.radix;
+    S.cyc_scan = (double)e->res.counters[20] / e->dev.grid;
+    S.cyc_process = (double)e->res.counters[21] / e->dev.grid;
+    S.cyc_barrier = (double)e->res.counters[22] / e->dev.grid;
+    S.cyc_process_max_block = (double)e->res.counters[23];
+    S.cyc_process_longest = (double)e->res.counters[24];
+    if (getenv("DFD_PROFILE_PRINT")) {
+        const unsigned long long* C = e->res.counters;
+        const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
+        for (int i = 0; i < EV_NTYPES; i++)
+            if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu  cycles/event %8.0f\n", names[i], C[4 + i], (double)C[32 + i] / C[4 + i]);
+        if (C[49]) fprintf(stderr, "  node activations %llu, cycles/activation %.0f\n", C[49], (double)C[48] / C[49]);
+        if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
+    }
     e->finished = true;
     return 0;
 }

@@ -42,8 +42,10 @@ struct __attribute__((aligned(16))) ChunkRec {
     uint32_t message_id;
     uint32_t packet_size;
     uint32_t total_size;
-    uint32_t chunk_id;
-    int32_t intm_grp_id;
+    uint16_t chunk_id;
+    uint16_t dst_grp;    // group of the destination router (carried so that no hop has to divide)
+    int16_t intm_grp_id;
+    uint16_t org_grp;    // group of origin_router
     uint32_t prev_lp;   // intm_lp_id as router id (last_hop LOCAL/GLOBAL) or source terminal id (TERMINAL)
     uint16_t prev_port; // vc_index of the upstream hop
     uint8_t prev_vc;    // output_chan of the upstream hop
@@ -58,7 +60,7 @@ struct __attribute__((aligned(16))) ChunkRec {
     uint32_t origin_router;
     uint32_t src_svr;  // sender_lp as svr id
     uint32_t dst_svr;  // final_dest_gid as svr id
-    uint32_t pad1;
+    uint32_t dst_router;  // router of dst_term
 };
 
 // 32-byte credit event (T_BUFFER / R_BUFFER)
@@ -83,8 +85,10 @@ struct __attribute__((aligned(16))) PoolSlot {
     uint32_t next_stop;   // router id or terminal id
     uint32_t pad;
     uint32_t packet_id, src_term, dst_term, message_id;
-    uint32_t packet_size, total_size, chunk_id;
-    int32_t intm_grp_id;
+    uint32_t packet_size, total_size;
+    uint16_t chunk_id, dst_grp;
+    int16_t intm_grp_id;
+    uint16_t org_grp;
     uint32_t prev_lp;
     uint16_t prev_port;
     uint8_t prev_vc;
@@ -96,7 +100,7 @@ struct __attribute__((aligned(16))) PoolSlot {
     uint8_t pad0;
     double travel_start_time;
     double msg_start_time;
-    uint32_t origin_router, src_svr, dst_svr, pad1;
+    uint32_t origin_router, src_svr, dst_svr, dst_router;
 };
 
 // entry of a router's private event heap (24 bytes)
@@ -134,7 +138,8 @@ struct __attribute__((aligned(16))) RouterHdr {
     uint32_t seq;
     uint32_t heap_n;
     uint32_t pool_free;  // head of the free list
-    uint32_t cin_head, kin_head;
+    uint32_t gid;        // codes_mapping gid of this router
+    uint16_t lid, grp;   // id inside the group, group id
     uint32_t pool_used, pool_hwm, heap_hwm;
     unsigned long long events;
     unsigned long long rng_draws;
@@ -164,7 +169,8 @@ struct SchedReq {
 // one chunk waiting in terminal_msgs (dally:5653-5680), 40 bytes
 struct TermChunk {
     uint32_t dst_svr, packet_id, packet_size, total_size, message_id, chunk_id;
-    uint32_t flags, pad;
+    uint32_t flags;  // bit0/1: remote/local event; bits 16..31: destination group
+    uint32_t dst_router;
     double msg_start_time;
 };
 
@@ -177,7 +183,7 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t svr_seq, term_seq;
     int32_t msg_sent_count, warm_msg_sent_count, msg_recvd_count, local_recvd_count;
     int32_t dest_id;
-    int32_t pad0;
+    uint32_t router;     // router this terminal hangs off
     long long rperm_data;
     double last_send_ts;
     double max_server_latency, sum_server_latency;
@@ -194,7 +200,7 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t tq_head, tq_count;  // terminal_msgs ring
     uint32_t nev;                // number of pending self events
     uint32_t cin_head, kin_head;
-    uint32_t pad1;
+    uint32_t grp;        // group of `router`
     double terminal_available_time, last_buf_full, busy_time;
     unsigned long long link_traffic, total_msg_size;
     uint32_t total_chunks, stalled_chunks, injected_chunks, ejected_chunks;
@@ -209,6 +215,7 @@ struct __attribute__((aligned(16))) NodeState {
     unsigned long long rng_draws;
     // global counters contributed by this node (packet_generate dally:5601-5615, packet_arrive :6512-6522)
     uint32_t local_sr, local_sg, remote_pk, minimal_count, nonmin_count, pad2;
+    uint32_t svr_gid, term_gid, pad3, pad4;
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)
@@ -224,6 +231,12 @@ struct DfdParams {
     int credit_size;
     double nic_seq_delay, lookahead, codes_cn_delay;
     double window, ts_end;
+    // host-precomputed values of bytes_to_ns()/reciprocals (same IEEE operations as the device would do)
+    double inj_chunk_cn, inj_chunk_local, inj_chunk_global;  // bytes_to_ns(chunk_size, bw)
+    double inj_pay_cn, inj_pay_local, inj_pay_global;        // bytes_to_ns(payload_sz % chunk_size, bw)
+    double inj_packet_cn;                                    // bytes_to_ns(payload_sz, cn_bw) (nic_ts of packet_generate)
+    double inv_cn_bw;                                        // 1 / cn_bandwidth
+    unsigned long long magic_p, magic_a;                     // floor(2^64/d)+1: n/d == __umul64hi(n, magic) for n < 2^32, d > 1
     int traffic, num_msgs, payload_sz;
     long long rperm_threshold;
     double warm_up_time, mean_interval;

@@ -51,6 +51,9 @@ typedef struct dfd_summary {
     unsigned long long h2d_bytes, d2h_bytes, device_bytes;
     int grid_blocks, block_threads, num_sms;
     int num_terminals, num_routers, radix;
+    /* cycle accounting of the window kernel, averaged over blocks: scan / process / barrier wait per run, the
+     * largest per-block process total, and the longest single process phase */
+    double cyc_scan, cyc_process, cyc_barrier, cyc_process_max_block, cyc_process_longest;
 } dfd_summary;
 
 void dfd_synthetic_opts_default(dfd_synthetic_opts* o);
