@@ -29,7 +29,7 @@
 
 #define INF_BITS 0x7FF0000000000000ULL
 #define NIL 0xFFFFFFFFu
-#define DFD_BLOCK 256
+#define DFD_BLOCK 128
 
 __device__ __forceinline__ double bits2d(unsigned long long b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ unsigned long long d2bits(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -41,6 +41,7 @@ struct Ctx {
     double t_end;
     double cand;  // min timestamp of everything this thread left pending or pushed this window
     int cur, nxt;
+    unsigned widx;
     unsigned* ev;  // per-block event counters by type (shared memory)
 };
 #define COUNT_EV(c, t) atomicAdd(&(c).ev[t], 1u)
@@ -584,6 +585,9 @@ __device__ void node_process(Ctx& c, unsigned n) {
     long long prof_lp0 = clock64();
 #endif
     NodeState* s = &A.node[n];
+#ifdef DFD_PROFILE
+    unsigned long long ev0 = s->events;
+#endif
     NodeEv* list = &A.nev[(size_t)n * P.nev_cap];
     const unsigned cmask = P.ncin_cap - 1, kmask = P.nkin_cap - 1;
     double next_ts;
@@ -674,8 +678,12 @@ __device__ void node_process(Ctx& c, unsigned n) {
     A.wake_self[n] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
 #ifdef DFD_PROFILE
-    atomicAdd(&A.counters[48], (unsigned long long)(clock64() - prof_lp0));
-    atomicAdd(&A.counters[49], 1ULL);
+    {
+        unsigned long long dt = (unsigned long long)(clock64() - prof_lp0);
+        atomicAdd(&A.counters[48], dt);
+        atomicAdd(&A.counters[49], 1ULL);
+        atomicMax(&A.winmax[c.widx & 0xFFFF], (dt << 16) | ((unsigned long long)min(255u, (unsigned)(s->events - ev0)) << 8) | 0ULL);
+    }
 #endif
 }
 
@@ -690,59 +698,145 @@ struct RCtx {
     PortState* port;
     PortQ* pq;
     PoolSlot* pool;
-    RHeapEnt* heap;
+    double* pts;       // far pending list: timestamps
+    RPendMeta* pmeta;  // far pending list: keys / payload references
+    double* nts;       // near pending list
+    RPendMeta* nmeta;
+    double near_limit; // entries with ts below this go to the near list
 };
 
-__device__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
+// Pending events of a router: a small "near" list (everything due before near_limit = window end + a few
+// windows) and a "far" list whose exact minimum is cached in the header.  The far list is only scanned when
+// its minimum drops below near_limit; the near list is what the event loop searches.
+__device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
     if (ts >= c.P->ts_end) return;
-    unsigned n = R.h->heap_n;
-    if (n >= (unsigned)c.P->rheap_cap) {
-        set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
-        return;
-    }
-    RHeapEnt* H = R.heap;
-    unsigned i = n;
-    while (i > 0) {
-        unsigned p = (i - 1) >> 1;
-        RHeapEnt pe = H[p];
-        if (!key_less(ts, src, seq, pe.ts, pe.src, pe.seq)) break;
-        H[i] = pe;
-        i = p;
-    }
-    H[i].ts = ts;
-    H[i].src = src;
-    H[i].seq = seq;
-    H[i].ref = ref;
-    R.h->heap_n = n + 1;
-    if (n + 1 > R.h->heap_hwm) R.h->heap_hwm = n + 1;
-}
-__device__ RHeapEnt rheap_pop(RCtx& R) {
-    RHeapEnt* H = R.heap;
-    RHeapEnt top = H[0];
-    unsigned n = --R.h->heap_n;
-    if (n > 0) {
-        RHeapEnt last = H[n];
-        unsigned i = 0;
-        for (;;) {
-            unsigned l = 2 * i + 1;
-            if (l >= n) break;
-            unsigned rr = l + 1;
-            unsigned m = l;
-            RHeapEnt me = H[l];
-            if (rr < n) {
-                RHeapEnt re = H[rr];
-                if (key_less(re.ts, re.src, re.seq, me.ts, me.src, me.seq)) {
-                    m = rr;
-                    me = re;
-                }
-            }
-            if (!key_less(me.ts, me.src, me.seq, last.ts, last.src, last.seq)) break;
-            H[i] = me;
-            i = m;
+    RPendMeta me;
+    me.src = src;
+    me.seq = seq;
+    me.ref = ref;
+    me.pad = 0;
+    if (ts < R.near_limit) {
+        unsigned n = R.h->near_n;
+        if (n >= (unsigned)c.P->rheap_cap) {
+            set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
+            return;
         }
-        H[i] = last;
+        R.nts[n] = ts;
+        *(uint4*)&R.nmeta[n] = *(uint4*)&me;
+        R.h->near_n = n + 1;
+    } else {
+        unsigned n = R.h->far_n;
+        if (n >= (unsigned)c.P->rheap_cap) {
+            set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
+            return;
+        }
+        R.pts[n] = ts;
+        *(uint4*)&R.pmeta[n] = *(uint4*)&me;
+        R.h->far_n = n + 1;
+        if (ts < R.h->far_min) R.h->far_min = ts;
+        if (n + 1 > R.h->heap_hwm) R.h->heap_hwm = n + 1;
     }
-    return top;
+}
+// move every far entry that is due before near_limit to the near list and recompute the far minimum; the
+// timestamps are fetched eight at a time so that the loads overlap
+__device__ void rpend_refill(Ctx& c, RCtx& R) {
+    unsigned n = R.h->far_n;
+    double* t = R.pts;
+    double fmin_ = DINF;
+    unsigned i = 0;
+    const double lim = R.near_limit;
+    while (i < n) {
+        double v[8];
+        unsigned cnt = min(8u, n - i);
+        if (cnt == 8) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                double2 d = *(const double2*)&t[i + 2 * k];
+                v[2 * k] = d.x;
+                v[2 * k + 1] = d.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (unsigned)k < cnt ? t[i + k] : DINF;
+        }
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) any |= v[k] < lim;
+        if (!any) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) fmin_ = fmin(fmin_, v[k]);
+            i += cnt;
+            continue;
+        }
+        // slow path for this batch: move due entries out one by one (the hole is filled from the end, and the
+        // entry that lands in it is examined next)
+        unsigned j = i;
+        while (j < i + cnt && j < n) {
+            double tv = t[j];
+            if (tv < lim) {
+                unsigned m = R.h->near_n;
+                if (m >= (unsigned)c.P->rheap_cap) {
+                    set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
+                    return;
+                }
+                R.nts[m] = tv;
+                *(uint4*)&R.nmeta[m] = *(const uint4*)&R.pmeta[j];
+                R.h->near_n = m + 1;
+                n--;
+                if (j != n) {
+                    t[j] = t[n];
+                    *(uint4*)&R.pmeta[j] = *(const uint4*)&R.pmeta[n];
+                }
+            } else {
+                fmin_ = fmin(fmin_, tv);
+                j++;
+            }
+        }
+        i = j;
+    }
+    R.h->far_n = n;
+    R.h->far_min = fmin_;
+}
+// index of the earliest near entry by (ts, src, seq); n must be > 0
+__device__ __forceinline__ unsigned rnear_min(const RCtx& R, unsigned n, double* ts_out) {
+    const double* t = R.nts;
+    double best = t[0];
+    unsigned bi = 0;
+    bool tie = false;
+    for (unsigned i = 1; i < n; i++) {
+        double v = t[i];
+        if (v < best) {
+            best = v;
+            bi = i;
+            tie = false;
+        } else if (v == best)
+            tie = true;
+    }
+    if (tie) {  // rare: equal timestamps -> order by (sender gid, sender sequence)
+        unsigned bsrc = 0, bseq = 0;
+        bool first = true;
+        for (unsigned k = 0; k < n; k++) {
+            if (t[k] != best) continue;
+            RPendMeta m = R.nmeta[k];
+            if (first || m.src < bsrc || (m.src == bsrc && m.seq < bseq)) {
+                bi = k;
+                bsrc = m.src;
+                bseq = m.seq;
+                first = false;
+            }
+        }
+    }
+    *ts_out = best;
+    return bi;
+}
+__device__ __forceinline__ unsigned rnear_take(RCtx& R, unsigned idx) {  // remove near entry idx, return its payload reference
+    unsigned ref = R.nmeta[idx].ref;
+    unsigned n = --R.h->near_n;
+    if (idx != n) {
+        R.nts[idx] = R.nts[n];
+        *(uint4*)&R.nmeta[idx] = *(const uint4*)&R.nmeta[n];
+    }
+    return ref;
 }
 
 // --- connection queries (DragonflyConnectionManager, dragonfly-network-manager.cxx) ----------------
@@ -1159,42 +1253,26 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
     double injection_ts = ps.noat - now;
     double propagation_ts = injection_ts + propagation_delay;
     {
-        ChunkRec rec;
-        rec.ts = now + propagation_ts;
-        rec.src = R.gid;
-        rec.seq = R.h->seq++;
-        rec.packet_id = m.packet_id;
-        rec.src_term = m.src_term;
-        rec.dst_term = m.dst_term;
-        rec.message_id = m.message_id;
-        rec.packet_size = m.packet_size;
-        rec.total_size = m.total_size;
-        rec.chunk_id = m.chunk_id;
-        rec.dst_grp = m.dst_grp;
-        rec.intm_grp_id = m.intm_grp_id;
-        rec.org_grp = m.org_grp;
-        rec.prev_lp = R.r;  // intm_lp_id
-        rec.prev_port = m.out_port;
-        rec.prev_vc = m.out_vc;
-        rec.last_hop = global ? DFD_HOP_GLOBAL : DFD_HOP_LOCAL;
-        rec.path_type = m.path_type;
-        rec.is_intm_visited = m.is_intm_visited;
-        rec.n_hop = m.n_hop;
-        rec.l_hop = m.l_hop;
-        rec.g_hop = m.g_hop;
-        rec.hops_cur_group = m.hops_cur_group;
-        rec.flags = m.flags;
-        rec.pad0 = 0;
-        rec.travel_start_time = m.travel_start_time;
-        rec.msg_start_time = m.msg_start_time;
-        rec.origin_router = m.origin_router;
-        rec.src_svr = m.src_svr;
-        rec.dst_svr = m.dst_svr;
-        rec.dst_router = m.dst_router;
+        // outgoing record = the pool slot with a new key and the "previous hop" fields replaced; the two
+        // layouts agree from byte 16 on, so this is a vector copy plus two patched words
+        union {
+            ChunkRec rec;
+            int4 v[6];
+        } u;
+        const int4* sv = (const int4*)&m;
+#pragma unroll
+        for (int i = 1; i < 6; i++) u.v[i] = sv[i];
+        u.rec.ts = now + propagation_ts;
+        u.rec.src = R.gid;
+        u.rec.seq = R.h->seq++;
+        u.rec.prev_lp = R.r;  // intm_lp_id
+        u.rec.prev_port = m.out_port;
+        u.rec.prev_vc = m.out_vc;
+        u.rec.last_hop = global ? DFD_HOP_GLOBAL : DFD_HOP_LOCAL;
         if (to_terminal)
-            push_chunk_to_node(c, m.next_stop, rec);
+            push_chunk_to_node(c, m.next_stop, u.rec);
         else
-            push_chunk_to_router(c, m.next_stop, rec);
+            push_chunk_to_router(c, m.next_stop, u.rec);
     }
     if ((tail || m.packet_size == 0) && (m.chunk_id == nchunks - 1))
         ps.link_traffic += tail;
@@ -1260,8 +1338,15 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     R.port = &A.port[(size_t)r * P.radix];
     R.pq = &A.portq[(size_t)r * P.radix];
     R.pool = &A.pool[(size_t)r * P.rpool_cap];
-    R.heap = &A.rheap[(size_t)r * P.rheap_cap];
+    R.pts = &A.rts[(size_t)r * P.rheap_cap];
+    R.pmeta = &A.rmeta[(size_t)r * P.rheap_cap];
+    R.nts = &A.nts[(size_t)r * P.rheap_cap];
+    R.nmeta = &A.nmeta[(size_t)r * P.rheap_cap];
+    R.near_limit = c.t_end + 4.0 * P.window;
     // drain the inbox filled during the previous window: chunks go to pool slots, keys to the heap
+#ifdef DFD_PROFILE
+    long long pd0 = clock64();
+#endif
     if (ntail_c) {
         const ChunkRec* in = &A.rcin[((size_t)c.cur * P.NR + r) * P.rcin_cap];
         for (unsigned i = 0; i < ntail_c; i++) {
@@ -1272,7 +1357,6 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
             }
             R.h->pool_free = R.pool[slot].next;
             R.h->pool_used++;
-            if (R.h->pool_used > R.h->pool_hwm) R.h->pool_hwm = R.h->pool_used;
             int4 v0 = __ldcg((const int4*)&in[i]);
             int4* dst = (int4*)&R.pool[slot];
 #pragma unroll
@@ -1293,33 +1377,57 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
         }
         A.rkin_tail[(size_t)c.cur * P.NR + r] = 0;
     }
-    while (R.h->heap_n > 0 && R.heap[0].ts < c.t_end) {
-        RHeapEnt e = rheap_pop(R);
-        double now = e.ts;
-        R.h->events++;
-        unsigned kind = e.ref >> 28;
+#ifdef DFD_PROFILE
+    if (ntail_c | ntail_k) {
+        atomicAdd(&A.counters[56], (unsigned long long)(clock64() - pd0));
+        atomicAdd(&A.counters[57], (unsigned long long)(ntail_c + ntail_k));
+    }
+#endif
+#ifdef DFD_PROFILE
+    unsigned prof_nev = 0;
+#endif
+    if (R.h->far_min < R.near_limit) rpend_refill(c, R);
+    double next_ts = DINF;
+    for (;;) {
+        unsigned np = R.h->near_n;
+        if (np == 0) break;
+        double now;
+        unsigned idx = rnear_min(R, np, &now);
+        if (!(now < c.t_end)) {
+            next_ts = now;
+            break;
+        }
+        unsigned ref = rnear_take(R, idx);
+#ifdef DFD_PROFILE
+        prof_nev++;
+#endif
+        unsigned kind = ref >> 28;
         PROF_T0();
         if (kind == RK_CHUNK) {
             COUNT_EV(c, EV_R_ARRIVE);
-            router_packet_receive(c, R, now, e.ref & 0x0FFFFFFFu);
+            router_packet_receive(c, R, now, ref & 0x0FFFFFFFu);
             PROF_ADD(c, EV_R_ARRIVE);
         } else if (kind == RK_CREDIT) {
             COUNT_EV(c, EV_R_BUFFER);
-            router_buf_update(c, R, now, e.ref & 0xFFFFu, (e.ref >> 16) & 0xFFu);
+            router_buf_update(c, R, now, ref & 0xFFFFu, (ref >> 16) & 0xFFu);
             PROF_ADD(c, EV_R_BUFFER);
         } else {
             COUNT_EV(c, EV_R_SEND);
-            router_packet_send(c, R, now, e.ref & 0xFFFFu);
+            router_packet_send(c, R, now, ref & 0xFFFFu);
             PROF_ADD(c, EV_R_SEND);
         }
     }
-    double next_ts = R.h->heap_n ? R.heap[0].ts : DINF;
+    next_ts = fmin(next_ts, R.h->far_min);
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
 #ifdef DFD_PROFILE
-    atomicAdd(&A.counters[50], (unsigned long long)(clock64() - prof_lp0));
-    atomicAdd(&A.counters[51], 1ULL);
-    if (ntail_c | ntail_k) atomicAdd(&A.counters[52], 1ULL);
+    {
+        unsigned long long dt = (unsigned long long)(clock64() - prof_lp0);
+        atomicAdd(&A.counters[50], dt);
+        atomicAdd(&A.counters[51], 1ULL);
+        if (ntail_c | ntail_k) atomicAdd(&A.counters[52], 1ULL);
+        atomicMax(&A.winmax[c.widx & 0xFFFF], (dt << 16) | ((unsigned long long)min(255u, prof_nev) << 8) | ((ntail_c | ntail_k) ? 3ULL : 1ULL));
+    }
 #endif
 }
 
@@ -1370,22 +1478,45 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
     long long t_scan = 0, t_proc = 0, t_bar = 0, t_procmax = 0;  // cycle accounting (thread 0 of each block)
     for (;;) {
         long long c0 = clock64();
+        // one L2 round trip: next window start, error flag and this thread's first wake words are all requested
+        // before any of them is consumed
+        const int cur = (int)(w & 1);
+        const unsigned nA = n0 + tid, rA = r0 + tid;
         unsigned long long tb = __ldcg(&A.gmin[w % 3]);
-        if (tb >= INF_BITS || __ldcg(&A.counters[2]) != 0 || w >= w_stop) break;
+        unsigned long long errw = __ldcg(&A.counters[2]);
+        unsigned long long wiA = INF_BITS, wsA = INF_BITS, wsR = INF_BITS;
+        unsigned tcA = 0, tkA = 0;
+        if (nA < n1) {
+            wiA = __ldcg(&A.wake_in[(size_t)cur * P.NT + nA]);
+            wsA = A.wake_self[nA];
+        }
+        if (rA < r1) {
+            tcA = __ldcg(&A.rcin_tail[(size_t)cur * P.NR + rA]);
+            tkA = __ldcg(&A.rkin_tail[(size_t)cur * P.NR + rA]);
+            wsR = A.wake_self[P.NT + rA];
+        }
+        if (tb >= INF_BITS || errw != 0 || w >= w_stop) break;
         double T = bits2d(tb);
         if (T >= P.ts_end) break;
         c.t_end = T + P.window;
-        c.cur = (int)(w & 1);
-        c.nxt = c.cur ^ 1;
+        c.cur = cur;
+        c.nxt = cur ^ 1;
+        c.widx = (unsigned)w;
         c.cand = DINF;
         if (blockIdx.x == 0 && tid == 0) __stcg(&A.gmin[(w + 2) % 3], INF_BITS);
         const unsigned long long te_bits = d2bits(c.t_end);
         // (1) scan + compact
-        for (unsigned n = n0 + tid; n < n1; n += nth) {
-            unsigned long long ws = A.wake_self[n];
-            unsigned long long wi = __ldcg(&A.wake_in[(size_t)c.cur * P.NT + n]);
+        for (unsigned n = nA; n < n1; n += nth) {
+            unsigned long long ws, wi;
+            if (n == nA) {
+                ws = wsA;
+                wi = wiA;
+            } else {
+                ws = A.wake_self[n];
+                wi = __ldcg(&A.wake_in[(size_t)cur * P.NT + n]);
+            }
             if (wi != INF_BITS) {
-                __stcg(&A.wake_in[(size_t)c.cur * P.NT + n], INF_BITS);
+                __stcg(&A.wake_in[(size_t)cur * P.NT + n], INF_BITS);
                 if (wi < ws) {
                     ws = wi;
                     A.wake_self[n] = ws;
@@ -1396,10 +1527,18 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
             else
                 c.cand = fmin(c.cand, bits2d(ws));
         }
-        for (unsigned r = r0 + tid; r < r1; r += nth) {
-            unsigned long long ws = A.wake_self[P.NT + r];
-            unsigned tc = __ldcg(&A.rcin_tail[(size_t)c.cur * P.NR + r]);
-            unsigned tk = __ldcg(&A.rkin_tail[(size_t)c.cur * P.NR + r]);
+        for (unsigned r = rA; r < r1; r += nth) {
+            unsigned long long ws;
+            unsigned tc, tk;
+            if (r == rA) {
+                ws = wsR;
+                tc = tcA;
+                tk = tkA;
+            } else {
+                ws = A.wake_self[P.NT + r];
+                tc = __ldcg(&A.rcin_tail[(size_t)cur * P.NR + r]);
+                tk = __ldcg(&A.rkin_tail[(size_t)cur * P.NR + r]);
+            }
             if (tc | tk | (unsigned)(ws < te_bits)) {
                 unsigned pos = atomicAdd(&s_n, 1u);
                 s_list[pos] = 0x80000000u | r;
@@ -1521,6 +1660,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         memset(h, 0, sizeof(RouterHdr));
         seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
         h->pool_free = 0;
+        h->far_min = bits2d(INF_BITS);
         h->gid = rtr_gid(P, r);
         h->lid = (uint16_t)(r % P.a);
         h->grp = (uint16_t)(r / P.a);
@@ -1600,12 +1740,17 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     if (dalloc(dev, &A.port, NR * P.radix)) return 1;
     if (dalloc(dev, &A.portq, NR * P.radix)) return 1;
     if (dalloc(dev, &A.pool, NR * P.rpool_cap)) return 1;
-    if (dalloc(dev, &A.rheap, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.rts, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.rmeta, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.nts, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.nmeta, NR * P.rheap_cap)) return 1;
     if (dalloc(dev, &A.rcin, 2 * NR * P.rcin_cap)) return 1;
     if (dalloc(dev, &A.rkin, 2 * NR * P.rkin_cap)) return 1;
     if (dalloc(dev, &A.rcin_tail, 2 * NR)) return 1;
     if (dalloc(dev, &A.rkin_tail, 2 * NR)) return 1;
     if (dalloc(dev, &A.counters, 64)) return 1;
+    if (dalloc(dev, &A.winmax, 65536)) return 1;
+    CK(cudaMemset(A.winmax, 0, 65536 * sizeof(unsigned long long)));
     int *loc_off, *loc_port, *loc_dest, *gs_port, *gs_group, *gdest, *routed_off, *routed_lid;
     if (dalloc(dev, &loc_off, T.loc_off.size())) return 1;
     if (dalloc(dev, &loc_port, T.loc_port.size())) return 1;
@@ -1707,6 +1852,8 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st) {
     CK(cudaMemcpyAsync(out->ack_first.data(), A.ack_first, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->ack_last.data(), A.ack_last, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost, st));
+    out->winmax.resize(65536);
+    CK(cudaMemcpyAsync(out->winmax.data(), A.winmax, sizeof(unsigned long long) * 65536, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     out->d2h_bytes = sizeof(NodeState) * (size_t)P.NT + sizeof(RouterHdr) * (size_t)P.NR + sizeof(PortState) * (size_t)P.NR * P.radix +
                      (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * (size_t)P.NT + sizeof(unsigned long long) * 32;

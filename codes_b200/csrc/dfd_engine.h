@@ -23,6 +23,7 @@ struct DfdHostResults {
     std::vector<unsigned> ack_count;
     std::vector<unsigned long long> ack_first, ack_last;
     unsigned long long counters[64];
+    std::vector<unsigned long long> winmax;
     size_t d2h_bytes = 0;
 };
 

@@ -926,7 +926,7 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->rcin_cap = (int)in_chunks;
     P->rkin_cap = (int)out_chunks;
     P->rpool_cap = (int)(in_chunks + out_chunks);
-    P->rheap_cap = (int)(in_chunks + out_chunks + p.radix);
+    P->rheap_cap = (int)((in_chunks + out_chunks + p.radix + 1) & ~1LL);  // even: scanned two timestamps per load
     return 0;
 }
 
@@ -1033,6 +1033,22 @@ int dfd_engine_finish(dfd_engine* e, void* stream) {
         for (int i = 0; i < EV_NTYPES; i++)
             if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu  cycles/event %8.0f\n", names[i], C[4 + i], (double)C[32 + i] / C[4 + i]);
         if (C[49]) fprintf(stderr, "  node activations %llu, cycles/activation %.0f\n", C[49], (double)C[48] / C[49]);
+        {
+            double sum[4] = {0, 0, 0, 0}, sumev[4] = {0, 0, 0, 0};
+            unsigned long long cnt[4] = {0, 0, 0, 0};
+            for (unsigned long long v : e->res.winmax) {
+                if (!v) continue;
+                int k = (int)(v & 3);
+                sum[k] += (double)(v >> 16);
+                sumev[k] += (double)((v >> 8) & 0xFF);
+                cnt[k]++;
+            }
+            const char* kn[4] = {"node", "router", "?", "router+drain"};
+            for (int k = 0; k < 4; k++)
+                if (cnt[k]) fprintf(stderr, "  slowest activation of the window is a %-12s in %6llu windows: avg %.0f cycles, %.1f events\n", kn[k], cnt[k], sum[k] / cnt[k], sumev[k] / cnt[k]);
+        }
+        if (C[54]) fprintf(stderr, "  rpend_min calls %llu, cycles/call %.0f, avg entries %.1f\n", C[54], (double)C[53] / C[54], (double)C[55] / C[54]);
+        if (C[57]) fprintf(stderr, "  drained records %llu, cycles/record %.0f\n", C[57], (double)C[56] / C[57]);
         if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
     }
     e->finished = true;

@@ -103,9 +103,9 @@ struct __attribute__((aligned(16))) PoolSlot {
     uint32_t origin_router, src_svr, dst_svr, dst_router;
 };
 
-// entry of a router's private event heap (24 bytes)
-struct RHeapEnt {
-    double ts;
+// A router's pending events live in an unsorted structure-of-arrays list: timestamps in one array (scanned
+// with independent 16-byte loads to find the minimum), tie-break key + payload reference in another.
+struct __attribute__((aligned(16))) RPendMeta {
     uint32_t src;
     uint32_t seq;
     uint32_t ref;  // kind<<28 | payload (pool slot / port | vc<<16)
@@ -136,12 +136,14 @@ struct __attribute__((aligned(16))) PortQ {
 struct __attribute__((aligned(16))) RouterHdr {
     int32_t rng[4];  // CLCG4 stream gid*3+0
     uint32_t seq;
-    uint32_t heap_n;
+    uint32_t far_n;      // entries of the far pending list
     uint32_t pool_free;  // head of the free list
     uint32_t gid;        // codes_mapping gid of this router
     uint16_t lid, grp;   // id inside the group, group id
-    uint32_t pool_used, pool_hwm, heap_hwm;
-    unsigned long long events;
+    uint32_t near_n;     // entries of the near pending list
+    uint32_t pool_used;
+    uint32_t heap_hwm;
+    double far_min;      // exact minimum timestamp of the far list (+inf when empty)
     unsigned long long rng_draws;
 };
 
@@ -270,7 +272,10 @@ struct DfdArrays {
     PortState* port;      // [NR][radix]
     PortQ* portq;         // [NR][radix]
     PoolSlot* pool;       // [NR][rpool_cap]
-    RHeapEnt* rheap;      // [NR][rheap_cap]
+    double* rts;          // [NR][rheap_cap]  far pending list: timestamps
+    RPendMeta* rmeta;     // [NR][rheap_cap]  far pending list: keys + payload references
+    double* nts;          // [NR][rheap_cap]  near pending list (due within a few windows)
+    RPendMeta* nmeta;     // [NR][rheap_cap]
     ChunkRec* rcin;       // [NR][rcin_cap]
     CreditRec* rkin;      // [NR][rkin_cap]
     unsigned* rcin_tail;  // [NR]
@@ -285,7 +290,8 @@ struct DfdArrays {
     const int* routed_off;  // [G*G+1]   CSR over (src group, dest group)
     const int* routed_lid;  // [..]      local id of the router owning each global link, inter-file order
     // run control / results
-    unsigned long long* counters;  // [16]: 0 events, 1 windows, 2 error code, 3 error info, 4.. per-type
+    unsigned long long* counters;  // [64]: 0 events, 1 windows, 2 error code, 3 error info, 4.. per-type, 20.. cycles
+    unsigned long long* winmax;    // [65536] profile builds: slowest LP activation of each window
 };
 
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,
