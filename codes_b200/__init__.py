@@ -90,6 +90,13 @@ ABI = [
     ("dfd_engine_run", _I, [_P, _P]),
     ("dfd_engine_finish", _I, [_P, _P]),
     ("dfd_tw_run", _I, [_P, _P]),
+    ("dfd_engine_set_partition", _I, [_P, _I, _I]),
+    ("dfd_engine_ipc_export", _I, [_P, _P]),
+    ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
+    ("dfd_engine_partition_bytes", _LL, [_P]),
+    ("dfd_engine_export_partition", _I, [_P, _P, _LL]),
+    ("dfd_engine_import_partition", _I, [_P, _P, _LL]),
+    ("dfd_engine_finalize", _I, [_P]),
     ("dfd_lp_io_flush", _I, [_P, _S]),
     ("dfd_model_net_report_stats", _I, [_P, _S, _I]),
     ("dfd_get_summary", _I, [_P, ctypes.POINTER(Summary)]),
@@ -221,6 +228,31 @@ class Engine:
     def tw_run(self, stream=None):
         self._ck(self._lib.dfd_tw_run(self._h, _P(stream or 0)))
 
+    # --- group-sharded runs (one process per GPU) ----------------------------------------------------
+    def set_partition(self, rank, world):
+        self._ck(self._lib.dfd_engine_set_partition(self._h, rank, world))
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(64)
+        self._ck(self._lib.dfd_engine_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_import(self, handles):
+        blob = b"".join(handles)
+        self._ck(self._lib.dfd_engine_ipc_import(self._h, blob, len(handles)))
+
+    def export_partition(self):
+        n = self._lib.dfd_engine_partition_bytes(self._h)
+        buf = ctypes.create_string_buffer(n)
+        self._ck(self._lib.dfd_engine_export_partition(self._h, buf, n))
+        return buf.raw
+
+    def import_partition(self, blob):
+        self._ck(self._lib.dfd_engine_import_partition(self._h, blob, len(blob)))
+
+    def finalize(self):
+        self._ck(self._lib.dfd_engine_finalize(self._h))
+
     # --- outputs -------------------------------------------------------------------------------------
     def lp_io_flush(self, directory):
         self._ck(self._lib.dfd_lp_io_flush(self._h, os.fsencode(directory)))
@@ -247,3 +279,34 @@ def run_synthetic(conf_path, lp_io_dir=None, **opts):
     if rc != 0:
         raise EngineError(err.value.decode(errors="replace"))
     return s
+
+
+def run_sharded(conf_path, dist, lp_io_dir=None, stream=None, **opts):
+    """Group-sharded run over the ranks of an initialised torch.distributed process group (one GPU per rank).
+    Every rank simulates its own dragonfly groups; rank 0 returns the merged Summary (other ranks return None)."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    eng = Engine()
+    eng.setup(conf_path, make_opts(**opts))
+    eng.set_partition(rank, world)
+    eng.upload(stream)
+    handles = [None] * world
+    dist.all_gather_object(handles, eng.ipc_export())
+    eng.ipc_import(handles)
+    import torch
+    torch.cuda.synchronize()
+    dist.barrier()
+    eng.run(stream)
+    eng.finish(stream)
+    parts = [None] * world
+    dist.gather_object(eng.export_partition(), parts if rank == 0 else None, dst=0)
+    out = None
+    if rank == 0:
+        for k in range(1, world):
+            eng.import_partition(parts[k])
+        eng.finalize()
+        if lp_io_dir:
+            eng.lp_io_flush(lp_io_dir)
+        out = eng.summary()
+    dist.barrier()
+    eng.close()
+    return out

@@ -40,8 +40,10 @@ struct Ctx {
     const DfdArrays* A;
     double t_end;
     double cand;  // min timestamp of everything this thread left pending or pushed this window
+    const DfdPeers* X;
     int cur, nxt;
     unsigned widx;
+    bool remote_writes;  // this thread wrote into another rank's memory during the window
     unsigned* ev;  // per-block event counters by type (shared memory)
 };
 #define COUNT_EV(c, t) atomicAdd(&(c).ev[t], 1u)
@@ -129,6 +131,18 @@ __device__ __forceinline__ bool key_less(double ts, unsigned src, unsigned seq, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// group sharding: which rank owns a group, and the address of one of its exchange arrays in my address space
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int owner_of_group(const DfdPeers& X, int g) {
+    int k = 0;
+    while (g >= X.grp_lo[k + 1]) k++;
+    return k;
+}
+template <typename T> __device__ __forceinline__ T* on_rank(const DfdPeers& X, T* local, int owner) {
+    return (T*)(X.base[owner] + ((char*)local - X.local_base));
+}
+
+// ------------------------------------------------------------------------------------------------
 // event delivery
 // ------------------------------------------------------------------------------------------------
 // chunk towards a router: append to the router's inbox of the NEXT window parity (drained by the
@@ -136,13 +150,24 @@ __device__ __forceinline__ bool key_less(double ts, unsigned src, unsigned seq, 
 __device__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
+    const DfdPeers& X = *c.X;
     if (rec.ts >= P.ts_end) return;
-    unsigned idx = atomicAdd(&A.rcin_tail[(size_t)c.nxt * P.NR + r], 1u);
+    unsigned* tail = &A.rcin_tail[(size_t)c.nxt * P.NR + r];
+    ChunkRec* box = &A.rcin[((size_t)c.nxt * P.NR + r) * P.rcin_cap];
+    unsigned idx;
+    int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(r, P.magic_a)) : X.rank;
+    if (owner != X.rank) {  // the router lives on another GPU: reserve and write through the NVLink mapping
+        tail = on_rank(X, tail, owner);
+        box = on_rank(X, box, owner);
+        idx = atomicAdd_system(tail, 1u);
+        c.remote_writes = true;
+    } else
+        idx = atomicAdd(tail, 1u);
     if (idx >= (unsigned)P.rcin_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
     }
-    int4* dst = (int4*)&A.rcin[((size_t)c.nxt * P.NR + r) * P.rcin_cap + idx];
+    int4* dst = (int4*)&box[idx];
     const int4* src = (const int4*)&rec;
 #pragma unroll
     for (int i = 0; i < 6; i++) __stcg(dst + i, src[i]);
@@ -151,8 +176,19 @@ __device__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
 __device__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
+    const DfdPeers& X = *c.X;
     if (ts >= P.ts_end) return;
-    unsigned idx = atomicAdd(&A.rkin_tail[(size_t)c.nxt * P.NR + r], 1u);
+    unsigned* tail = &A.rkin_tail[(size_t)c.nxt * P.NR + r];
+    CreditRec* box = &A.rkin[((size_t)c.nxt * P.NR + r) * P.rkin_cap];
+    unsigned idx;
+    int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(r, P.magic_a)) : X.rank;
+    if (owner != X.rank) {
+        tail = on_rank(X, tail, owner);
+        box = on_rank(X, box, owner);
+        idx = atomicAdd_system(tail, 1u);
+        c.remote_writes = true;
+    } else
+        idx = atomicAdd(tail, 1u);
     if (idx >= (unsigned)P.rkin_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
@@ -166,7 +202,7 @@ __device__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned sr
     rec.pad0 = 0;
     rec.pad1 = 0;
     rec.pad2 = 0;
-    int4* dst = (int4*)&A.rkin[((size_t)c.nxt * P.NR + r) * P.rkin_cap + idx];
+    int4* dst = (int4*)&box[idx];
     __stcg(dst, ((const int4*)&rec)[0]);
     __stcg(dst + 1, ((const int4*)&rec)[1]);
     c.cand = fmin(c.cand, ts);
@@ -318,9 +354,18 @@ __device__ void svr_remote(Ctx& c, unsigned n, NodeState* s, double now, unsigne
         if (packet_latency > s->max_server_latency) s->max_server_latency = packet_latency;
         s->svr_seq++;  // tw_event_new for the ACK
         if (now < P.ts_end) {
-            atomicAdd(&A.ack_count[src_svr], 1u);
-            atomicMin(&A.ack_first[src_svr], d2bits(now));
-            atomicMax(&A.ack_last[src_svr], d2bits(now));
+            const DfdPeers& X = *c.X;
+            int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(fastdiv(src_svr, P.magic_p), P.magic_a)) : X.rank;
+            if (owner != X.rank) {
+                atomicAdd_system(on_rank(X, &A.ack_count[src_svr], owner), 1u);
+                atomicMin_system(on_rank(X, &A.ack_first[src_svr], owner), d2bits(now));
+                atomicMax_system(on_rank(X, &A.ack_last[src_svr], owner), d2bits(now));
+                c.remote_writes = true;
+            } else {
+                atomicAdd(&A.ack_count[src_svr], 1u);
+                atomicMin(&A.ack_first[src_svr], d2bits(now));
+                atomicMax(&A.ack_last[src_svr], d2bits(now));
+            }
             COUNT_EV(c, EV_ACK);
         }
     }
@@ -1454,19 +1499,64 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 // slice's wake words compacts the LPs that have work into a shared-memory list, (2) the list is dealt out
 // warp-first (lane 0 of every warp, then lane 1, ...) so that concurrently active LPs do not serialise inside
 // one warp, (3) block-min of the next timestamps -> one atomicMin, (4) grid barrier.
-__global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, unsigned long long max_windows) {
+// Cross-GPU part of the window close (thread 0 of block 0, after the local barrier): publish this rank's
+// minimum and window count into every peer's sync block, wait for theirs, combine.  Bounded spin: a peer that
+// never arrives raises DFD_ERR_PEER_TIMEOUT instead of hanging the GPU.
+__device__ void peer_window_close(const DfdArrays& A, const DfdPeers& X, unsigned long long w) {
+    const unsigned slot = (unsigned)((w + 1) % 3);
+    unsigned long long m = __ldcg(&A.gmin[slot]);
+    unsigned long long myerr = __ldcg(&A.counters[2]);
+    DfdSync* mine = (DfdSync*)X.local_base;
+    __threadfence_system();
+    for (int k = 0; k < X.world; k++) {
+        if (k == X.rank) continue;
+        DfdSync* peer = (DfdSync*)X.base[k];
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&peer->mins[slot][X.rank]), "l"(m) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&peer->err[X.rank]), "l"(myerr) : "memory");
+    }
+    __threadfence_system();
+    for (int k = 0; k < X.world; k++) {
+        if (k == X.rank) continue;
+        DfdSync* peer = (DfdSync*)X.base[k];
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer->flag[X.rank]), "l"(w + 1) : "memory");
+    }
+    unsigned long long err = myerr;
+    for (int k = 0; k < X.world; k++) {
+        if (k == X.rank) continue;
+        unsigned long long f;
+        unsigned long long spins = 0;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&mine->flag[k]) : "memory");
+            if (++spins > (1ULL << 27)) {  // ~ a minute of polling
+                err = DFD_ERR_PEER_TIMEOUT;
+                break;
+            }
+        } while (f < w + 1);
+        unsigned long long pm, pe;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pm) : "l"(&mine->mins[slot][k]) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pe) : "l"(&mine->err[k]) : "memory");
+        if (pm < m) m = pm;
+        if (pe && !err) err = DFD_ERR_PEER_ERROR;
+    }
+    __stcg(&A.gmin[slot], m);
+    if (err && !myerr) set_error(A, (unsigned)err, 0);
+}
+
+__global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long max_windows) {
     extern __shared__ unsigned s_list[];  // [lps_per_block]: bit31 = router, low bits = index; then tc/tk halves
     __shared__ double s_min[DFD_BLOCK / 32];
     __shared__ unsigned s_ev[EV_NTYPES];
     __shared__ unsigned s_n;
     const unsigned tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
-    const unsigned ntb = (P.NT + gridDim.x - 1) / gridDim.x, nrb = (P.NR + gridDim.x - 1) / gridDim.x;
-    const unsigned n0 = min((unsigned)P.NT, blockIdx.x * ntb), n1 = min((unsigned)P.NT, n0 + ntb);
-    const unsigned r0 = min((unsigned)P.NR, blockIdx.x * nrb), r1 = min((unsigned)P.NR, r0 + nrb);
+    // this rank owns nodes [X.n0, X.n1) and routers [X.r0, X.r1); the block takes a contiguous slice of each
+    const unsigned ntb = ((unsigned)(X.n1 - X.n0) + gridDim.x - 1) / gridDim.x, nrb = ((unsigned)(X.r1 - X.r0) + gridDim.x - 1) / gridDim.x;
+    const unsigned n0 = min((unsigned)X.n1, X.n0 + blockIdx.x * ntb), n1 = min((unsigned)X.n1, n0 + ntb);
+    const unsigned r0 = min((unsigned)X.r1, X.r0 + blockIdx.x * nrb), r1 = min((unsigned)X.r1, r0 + nrb);
     unsigned* s_tails = s_list + (ntb + nrb);
     Ctx c;
     c.P = &P;
     c.A = &A;
+    c.X = &X;
     c.ev = s_ev;
     if (tid < EV_NTYPES) s_ev[tid] = 0;
     if (tid == 0) s_n = 0;
@@ -1503,6 +1593,7 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
         c.nxt = cur ^ 1;
         c.widx = (unsigned)w;
         c.cand = DINF;
+        c.remote_writes = false;
         if (blockIdx.x == 0 && tid == 0) __stcg(&A.gmin[(w + 2) % 3], INF_BITS);
         const unsigned long long te_bits = d2bits(c.t_end);
         // (1) scan + compact
@@ -1558,6 +1649,7 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
             } else
                 node_process(c, e);
         }
+        if (c.remote_writes) __threadfence_system();  // records written over NVLink must be visible before the flags
         // (3) block-min of the candidates, one atomicMin per block
         double v = c.cand;
         for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
@@ -1573,6 +1665,11 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
         long long c2 = clock64();
         nbar++;
         grid_barrier(&A.counters[29], (bar0 + nbar) * gridDim.x);
+        if (X.world > 1) {  // exchange minima / completion flags with the other GPUs, then release the local blocks
+            if (blockIdx.x == 0 && tid == 0) peer_window_close(A, X, w);
+            nbar++;
+            grid_barrier(&A.counters[29], (bar0 + nbar) * gridDim.x);
+        }
         long long c3 = clock64();
         t_scan += c1 - c0;
         t_proc += c2 - c1;
@@ -1706,10 +1803,33 @@ template <typename T> static int dalloc(DfdDevice* dev, T** p, size_t n) {
     return 0;
 }
 
-int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) {
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X) {
+    memset(X, 0, sizeof *X);
+    X->rank = rank;
+    X->world = world;
+    for (int k = 0; k <= world; k++) X->grp_lo[k] = (int)(((long long)k * G) / world);  // contiguous groups
+    for (int k = world + 1; k <= DFD_MAX_RANKS; k++) X->grp_lo[k] = G;
+    X->r0 = X->grp_lo[rank] * a;
+    X->r1 = X->grp_lo[rank + 1] * a;
+    X->n0 = X->r0 * p;
+    X->n1 = X->r1 * p;
+}
+
+int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world) {
     dev->P = P;
     DfdArrays& A = dev->A;
     memset(&A, 0, sizeof A);
+    if (world < 1 || world > DFD_MAX_RANKS || rank < 0 || rank >= world) {
+        snprintf(dev->error, sizeof dev->error, "bad partition: rank %d of %d (at most %d ranks)", rank, world, DFD_MAX_RANKS);
+        return 1;
+    }
+    if (world > P.G) {
+        snprintf(dev->error, sizeof dev->error, "more ranks (%d) than dragonfly groups (%d)", world, P.G);
+        return 1;
+    }
+    dfd_partition(P.G, P.a, P.p, rank, world, &dev->X);
     int devid = 0;
     CK(cudaGetDevice(&devid));
     cudaDeviceProp prop;
@@ -1733,9 +1853,6 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     if (dalloc(dev, &A.nkin, NT * P.nkin_cap)) return 1;
     if (dalloc(dev, &A.ncin_tail, NT)) return 1;
     if (dalloc(dev, &A.nkin_tail, NT)) return 1;
-    if (dalloc(dev, &A.ack_count, NT)) return 1;
-    if (dalloc(dev, &A.ack_first, NT)) return 1;
-    if (dalloc(dev, &A.ack_last, NT)) return 1;
     if (dalloc(dev, &A.rh, NR)) return 1;
     if (dalloc(dev, &A.port, NR * P.radix)) return 1;
     if (dalloc(dev, &A.portq, NR * P.radix)) return 1;
@@ -1744,10 +1861,37 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     if (dalloc(dev, &A.rmeta, NR * P.rheap_cap)) return 1;
     if (dalloc(dev, &A.nts, NR * P.rheap_cap)) return 1;
     if (dalloc(dev, &A.nmeta, NR * P.rheap_cap)) return 1;
-    if (dalloc(dev, &A.rcin, 2 * NR * P.rcin_cap)) return 1;
-    if (dalloc(dev, &A.rkin, 2 * NR * P.rkin_cap)) return 1;
-    if (dalloc(dev, &A.rcin_tail, 2 * NR)) return 1;
-    if (dalloc(dev, &A.rkin_tail, 2 * NR)) return 1;
+    // exchange region: everything another rank may write (router inboxes and their tails, ACK statistics), behind
+    // the sync block -- one allocation, one CUDA-IPC handle
+    size_t off = align256(sizeof(DfdSync));
+    size_t o_rcin = off;
+    off = align256(off + 2 * NR * P.rcin_cap * sizeof(ChunkRec));
+    size_t o_rkin = off;
+    off = align256(off + 2 * NR * P.rkin_cap * sizeof(CreditRec));
+    size_t o_rct = off;
+    off = align256(off + 2 * NR * sizeof(unsigned));
+    size_t o_rkt = off;
+    off = align256(off + 2 * NR * sizeof(unsigned));
+    size_t o_ac = off;
+    off = align256(off + NT * sizeof(unsigned));
+    size_t o_af = off;
+    off = align256(off + NT * sizeof(unsigned long long));
+    size_t o_al = off;
+    off = align256(off + NT * sizeof(unsigned long long));
+    char* xr = nullptr;
+    if (dalloc(dev, &xr, off)) return 1;
+    dev->xregion = xr;
+    dev->xregion_bytes = off;
+    A.rcin = (ChunkRec*)(xr + o_rcin);
+    A.rkin = (CreditRec*)(xr + o_rkin);
+    A.rcin_tail = (unsigned*)(xr + o_rct);
+    A.rkin_tail = (unsigned*)(xr + o_rkt);
+    A.ack_count = (unsigned*)(xr + o_ac);
+    A.ack_first = (unsigned long long*)(xr + o_af);
+    A.ack_last = (unsigned long long*)(xr + o_al);
+    for (int k = 0; k < DFD_MAX_RANKS; k++) dev->X.base[k] = nullptr;
+    dev->X.base[rank] = xr;
+    dev->X.local_base = xr;
     if (dalloc(dev, &A.counters, 64)) return 1;
     if (dalloc(dev, &A.winmax, 65536)) return 1;
     CK(cudaMemset(A.winmax, 0, 65536 * sizeof(unsigned long long)));
@@ -1776,11 +1920,12 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
     if (const char* ev = getenv("DFD_BLOCK_THREADS")) dev->block = std::max(32, std::min(DFD_BLOCK, atoi(ev) / 32 * 32));
     int lps_per_block = 16;
     if (const char* ev = getenv("DFD_LPS_PER_BLOCK")) lps_per_block = std::max(1, atoi(ev));
-    size_t want = (NLP + lps_per_block - 1) / lps_per_block;
+    const size_t ownT = dev->X.n1 - dev->X.n0, ownR = dev->X.r1 - dev->X.r0;
+    size_t want = (ownT + ownR + lps_per_block - 1) / lps_per_block;
     for (int iter = 0; iter < 2; iter++) {
         // dynamic shared memory depends on the slice size, which depends on the grid: settle in two passes
-        size_t g = iter == 0 ? want : (size_t)dev->grid;
-        size_t ntb = (NT + g - 1) / g, nrb = (NR + g - 1) / g;
+        size_t g = iter == 0 ? std::max<size_t>(1, want) : (size_t)dev->grid;
+        size_t ntb = (ownT + g - 1) / g, nrb = (ownR + g - 1) / g;
         dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
         if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
         int per_sm = 0;
@@ -1793,11 +1938,36 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T) 
         dev->grid = (int)std::max<size_t>(1, std::min(want, maxb));
         dev->blocks_per_sm = per_sm;
     }
-    if (const char* ev = getenv("DFD_GRID")) {
-        dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
-        size_t g = dev->grid, ntb = (NT + g - 1) / g, nrb = (NR + g - 1) / g;
+    if (const char* ev = getenv("DFD_GRID")) dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
+    {
+        size_t g = dev->grid, ntb = (ownT + g - 1) / g, nrb = (ownR + g - 1) / g;
         dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
         if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
+    }
+    return 0;
+}
+
+// CUDA-IPC plumbing of the exchange regions (one process per GPU)
+int dfd_device_ipc_export(DfdDevice* dev, void* handle64) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dev->xregion));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int dfd_device_ipc_import(DfdDevice* dev, const void* handles, int world) {
+    if (world != dev->X.world) {
+        snprintf(dev->error, sizeof dev->error, "ipc import: %d handles for a world of %d", world, dev->X.world);
+        return 1;
+    }
+    for (int k = 0; k < world; k++) {
+        if (k == dev->X.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + 64 * k, 64);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        dev->X.base[k] = (char*)ptr;
+        dev->ipc_opened.push_back(ptr);
     }
     return 0;
 }
@@ -1825,13 +1995,19 @@ int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st
 
 int dfd_device_reset(DfdDevice* dev, cudaStream_t st) {
     int blocks = dev->num_sms * 8;
+    CK(cudaMemsetAsync(dev->xregion, 0, sizeof(DfdSync), st));
     dfd_init_kernel<<<blocks, 256, 0, st>>>(dev->P, dev->A, dev->seeds);
     CK(cudaGetLastError());
     return 0;
 }
 
 int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windows) {
-    void* args[] = {(void*)&dev->P, (void*)&dev->A, (void*)&max_windows};
+    for (int k = 0; k < dev->X.world; k++)
+        if (!dev->X.base[k]) {
+            snprintf(dev->error, sizeof dev->error, "rank %d: the exchange region of rank %d has not been imported", dev->X.rank, k);
+            return 1;
+        }
+    void* args[] = {(void*)&dev->P, (void*)&dev->A, (void*)&dev->X, (void*)&max_windows};
     CK(cudaLaunchCooperativeKernel((void*)dfd_run_kernel, dim3(dev->grid), dim3(dev->block), args, dev->smem, st));
     return 0;
 }
@@ -1867,6 +2043,8 @@ int dfd_device_read_counters(DfdDevice* dev, unsigned long long* counters, cudaS
 }
 
 void dfd_device_destroy(DfdDevice* dev) {
+    for (void* p : dev->ipc_opened) cudaIpcCloseMemHandle(p);
+    dev->ipc_opened.clear();
     for (void* p : dev->allocs) cudaFree(p);
     dev->allocs.clear();
 }

@@ -31,6 +31,10 @@ struct DfdDevice {
     DfdParams P;
     DfdArrays A;
     DfdSeedConsts seeds;
+    DfdPeers X;
+    char* xregion = nullptr;
+    size_t xregion_bytes = 0;
+    std::vector<void*> ipc_opened;
     std::vector<void*> allocs;
     size_t bytes_allocated = 0, topo_bytes = 0;
     int num_sms = 0, grid = 0, block = 0, blocks_per_sm = 0;
@@ -38,7 +42,10 @@ struct DfdDevice {
     char error[512] = {0};
 };
 
-int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T);
+void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X);
+int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world);
+int dfd_device_ipc_export(DfdDevice* dev, void* handle64);
+int dfd_device_ipc_import(DfdDevice* dev, const void* handles, int world);
 int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st);
 int dfd_device_reset(DfdDevice* dev, cudaStream_t st);
 int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windows);

@@ -179,7 +179,8 @@ struct dfd_engine {
     std::string conf_path, conf_dir;
     Section root;
     bool loaded = false, registered = false, mapped = false, configured = false, opts_set = false;
-    bool device_ready = false, uploaded = false, finished = false;
+    bool device_ready = false, uploaded = false, finished = false, downloaded = false;
+    int rank = 0, world = 1;
     HostParams hp;
     dfd_synthetic_opts opts;
     double mean_interval = 0, load = 0;
@@ -980,7 +981,7 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
     }
     e->dev = DfdDevice();
     seed_consts(&e->dev.seeds);
-    if (dfd_device_create(&e->dev, P, e->topo)) return fail(e, "%s", e->dev.error);
+    if (dfd_device_create(&e->dev, P, e->topo, e->rank, e->world)) return fail(e, "%s", e->dev.error);
     e->device_ready = true;
     cudaStream_t st = (cudaStream_t)stream;
     if (dfd_device_upload_topo(&e->dev, e->topo, st)) return fail(e, "%s", e->dev.error);
@@ -1004,13 +1005,7 @@ int dfd_engine_run(dfd_engine* e, void* stream) {
     return 0;
 }
 
-int dfd_engine_finish(dfd_engine* e, void* stream) {
-    if (!e->uploaded) return fail(e, "engine_finish: engine_upload has not been called");
-    memset(&e->sum, 0, sizeof e->sum);
-    if (dfd_device_download(&e->dev, &e->res, (cudaStream_t)stream)) return fail(e, "%s", e->dev.error);
-    if (e->res.counters[2] != 0)
-        return fail(e, "device error %llu (%s), info 0x%llx", e->res.counters[2], device_error_name(e->res.counters[2]), e->res.counters[3]);
-    finalize(e);
+static void fill_summary_meta(dfd_engine* e) {
     dfd_summary& S = e->sum;
     S.window_ns = e->dev.P.window;
     S.h2d_bytes = e->h2d_bytes;
@@ -1027,30 +1022,135 @@ int dfd_engine_finish(dfd_engine* e, void* stream) {
     S.cyc_barrier = (double)e->res.counters[22] / e->dev.grid;
     S.cyc_process_max_block = (double)e->res.counters[23];
     S.cyc_process_longest = (double)e->res.counters[24];
-    if (getenv("DFD_PROFILE_PRINT")) {
-        const unsigned long long* C = e->res.counters;
-        const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
-        for (int i = 0; i < EV_NTYPES; i++)
-            if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu  cycles/event %8.0f\n", names[i], C[4 + i], (double)C[32 + i] / C[4 + i]);
-        if (C[49]) fprintf(stderr, "  node activations %llu, cycles/activation %.0f\n", C[49], (double)C[48] / C[49]);
-        {
-            double sum[4] = {0, 0, 0, 0}, sumev[4] = {0, 0, 0, 0};
-            unsigned long long cnt[4] = {0, 0, 0, 0};
-            for (unsigned long long v : e->res.winmax) {
-                if (!v) continue;
-                int k = (int)(v & 3);
-                sum[k] += (double)(v >> 16);
-                sumev[k] += (double)((v >> 8) & 0xFF);
-                cnt[k]++;
-            }
-            const char* kn[4] = {"node", "router", "?", "router+drain"};
-            for (int k = 0; k < 4; k++)
-                if (cnt[k]) fprintf(stderr, "  slowest activation of the window is a %-12s in %6llu windows: avg %.0f cycles, %.1f events\n", kn[k], cnt[k], sum[k] / cnt[k], sumev[k] / cnt[k]);
-        }
-        if (C[54]) fprintf(stderr, "  rpend_min calls %llu, cycles/call %.0f, avg entries %.1f\n", C[54], (double)C[53] / C[54], (double)C[55] / C[54]);
-        if (C[57]) fprintf(stderr, "  drained records %llu, cycles/record %.0f\n", C[57], (double)C[56] / C[57]);
-        if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
+}
+
+static void profile_print(dfd_engine* e) {
+    if (!getenv("DFD_PROFILE_PRINT")) return;
+    const unsigned long long* C = e->res.counters;
+    const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
+    for (int i = 0; i < EV_NTYPES; i++)
+        if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu  cycles/event %8.0f\n", names[i], C[4 + i], (double)C[32 + i] / C[4 + i]);
+    if (C[49]) fprintf(stderr, "  node activations %llu, cycles/activation %.0f\n", C[49], (double)C[48] / C[49]);
+    double sum[4] = {0, 0, 0, 0}, sumev[4] = {0, 0, 0, 0};
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    for (unsigned long long v : e->res.winmax) {
+        if (!v) continue;
+        int k = (int)(v & 3);
+        sum[k] += (double)(v >> 16);
+        sumev[k] += (double)((v >> 8) & 0xFF);
+        cnt[k]++;
     }
+    const char* kn[4] = {"node", "router", "?", "router+drain"};
+    for (int k = 0; k < 4; k++)
+        if (cnt[k]) fprintf(stderr, "  slowest activation of the window is a %-12s in %6llu windows: avg %.0f cycles, %.1f events\n", kn[k], cnt[k], sum[k] / cnt[k], sumev[k] / cnt[k]);
+    if (C[57]) fprintf(stderr, "  drained records %llu, cycles/record %.0f\n", C[57], (double)C[56] / C[57]);
+    if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
+}
+
+int dfd_engine_finish(dfd_engine* e, void* stream) {
+    if (!e->uploaded) return fail(e, "engine_finish: engine_upload has not been called");
+    memset(&e->sum, 0, sizeof e->sum);
+    if (dfd_device_download(&e->dev, &e->res, (cudaStream_t)stream)) return fail(e, "%s", e->dev.error);
+    if (e->res.counters[2] != 0)
+        return fail(e, "device error %llu (%s), info 0x%llx", e->res.counters[2], device_error_name(e->res.counters[2]), e->res.counters[3]);
+    e->downloaded = true;
+    if (e->world > 1) return 0;  // sharded run: rank 0 merges the partitions, then calls dfd_engine_finalize
+    finalize(e);
+    fill_summary_meta(e);
+    profile_print(e);
+    e->finished = true;
+    return 0;
+}
+
+// ---- group-sharded runs (one process per GPU) ---------------------------------------------------------
+int dfd_engine_set_partition(dfd_engine* e, int rank, int world) {
+    if (world < 1 || world > DFD_MAX_RANKS || rank < 0 || rank >= world) return fail(e, "bad partition: rank %d of %d (at most %d ranks)", rank, world, DFD_MAX_RANKS);
+    if (e->uploaded) return fail(e, "set_partition must be called before engine_upload");
+    e->rank = rank;
+    e->world = world;
+    return 0;
+}
+int dfd_engine_ipc_export(dfd_engine* e, void* handle64) {
+    if (!e->uploaded) return fail(e, "ipc_export: engine_upload has not been called");
+    if (dfd_device_ipc_export(&e->dev, handle64)) return fail(e, "%s", e->dev.error);
+    return 0;
+}
+int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world) {
+    if (!e->uploaded) return fail(e, "ipc_import: engine_upload has not been called");
+    if (dfd_device_ipc_import(&e->dev, handles, world)) return fail(e, "%s", e->dev.error);
+    return 0;
+}
+namespace {
+struct PartHeader {
+    int rank, n0, n1, r0, r1, radix;
+    unsigned long long counters[64];
+};
+}
+long long dfd_engine_partition_bytes(const dfd_engine* e) {
+    const DfdPeers& X = e->dev.X;
+    size_t nn = X.n1 - X.n0, nr = X.r1 - X.r0;
+    return (long long)(sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) +
+                       nr * (sizeof(RouterHdr) + (size_t)e->hp.radix * sizeof(PortState)));
+}
+int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len) {
+    if (!e->downloaded) return fail(e, "export_partition: engine_finish has not been called");
+    if (len < dfd_engine_partition_bytes(e)) return fail(e, "export_partition: buffer too small");
+    const DfdPeers& X = e->dev.X;
+    size_t nn = X.n1 - X.n0, nr = X.r1 - X.r0, radix = e->hp.radix;
+    char* p = (char*)buf;
+    PartHeader h;
+    memset(&h, 0, sizeof h);
+    h.rank = X.rank;
+    h.n0 = X.n0;
+    h.n1 = X.n1;
+    h.r0 = X.r0;
+    h.r1 = X.r1;
+    h.radix = (int)radix;
+    memcpy(h.counters, e->res.counters, sizeof h.counters);
+    memcpy(p, &h, sizeof h);
+    p += sizeof h;
+#define PUT(vec, off, cnt)                                   \
+    memcpy(p, (vec).data() + (off), (cnt) * sizeof((vec)[0])); \
+    p += (cnt) * sizeof((vec)[0]);
+    PUT(e->res.node, X.n0, nn)
+    PUT(e->res.ack_count, X.n0, nn)
+    PUT(e->res.ack_first, X.n0, nn)
+    PUT(e->res.ack_last, X.n0, nn)
+    PUT(e->res.rh, X.r0, nr)
+    PUT(e->res.port, (size_t)X.r0 * radix, nr * radix)
+#undef PUT
+    return 0;
+}
+int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
+    if (!e->downloaded) return fail(e, "import_partition: engine_finish has not been called");
+    if (len < (long long)sizeof(PartHeader)) return fail(e, "import_partition: truncated buffer");
+    const char* p = (const char*)buf;
+    PartHeader h;
+    memcpy(&h, p, sizeof h);
+    p += sizeof h;
+    size_t nn = h.n1 - h.n0, nr = h.r1 - h.r0, radix = e->hp.radix;
+    if (h.radix != (int)radix || h.n1 > e->hp.total_terminals || h.r1 > e->hp.total_routers || h.rank == e->rank)
+        return fail(e, "import_partition: partition does not belong to this run");
+    if (h.counters[2]) return fail(e, "rank %d reported device error %llu (%s)", h.rank, h.counters[2], device_error_name(h.counters[2]));
+#define GET(vec, off, cnt)                                   \
+    memcpy((vec).data() + (off), p, (cnt) * sizeof((vec)[0])); \
+    p += (cnt) * sizeof((vec)[0]);
+    GET(e->res.node, h.n0, nn)
+    GET(e->res.ack_count, h.n0, nn)
+    GET(e->res.ack_first, h.n0, nn)
+    GET(e->res.ack_last, h.n0, nn)
+    GET(e->res.rh, h.r0, nr)
+    GET(e->res.port, (size_t)h.r0 * radix, nr * radix)
+#undef GET
+    e->res.counters[0] += h.counters[0];  // committed events
+    for (int i = 0; i < EV_NTYPES; i++) e->res.counters[4 + i] += h.counters[4 + i];
+    return 0;
+}
+int dfd_engine_finalize(dfd_engine* e) {
+    if (!e->downloaded) return fail(e, "engine_finalize: engine_finish has not been called");
+    memset(&e->sum, 0, sizeof e->sum);
+    finalize(e);
+    fill_summary_meta(e);
     e->finished = true;
     return 0;
 }

@@ -294,6 +294,24 @@ struct DfdArrays {
     unsigned long long* winmax;    // [65536] profile builds: slowest LP activation of each window
 };
 
+// Group-sharded multi-GPU run: rank k owns the dragonfly groups [grp_lo[k], grp_lo[k+1]) with all
+// their routers, terminals and servers.  Only three things cross ranks: chunks and credits over global links
+// (written straight into the owner's router inbox through a CUDA-IPC mapping of its exchange region) and the
+// svr->svr ACK statistics.  One window = local grid barrier, flag + minimum exchange over NVLink, local barrier.
+#define DFD_MAX_RANKS 8
+struct DfdSync {                                   // lives at the start of every rank's exchange region
+    unsigned long long flag[DFD_MAX_RANKS];        // flag[k]: number of windows rank k has closed
+    unsigned long long mins[3][DFD_MAX_RANKS];     // mins[w%3][k]: rank k's earliest pending timestamp for window w
+    unsigned long long err[DFD_MAX_RANKS];         // err[k]: device error code raised on rank k
+};
+struct DfdPeers {
+    int rank, world;
+    int grp_lo[DFD_MAX_RANKS + 1];
+    int n0, n1, r0, r1;                 // owned node / router ranges
+    char* base[DFD_MAX_RANKS];          // exchange-region base of every rank as mapped into this process
+    char* local_base;                   // == base[rank]
+};
+
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,
        DFD_ERR_HEAP_OVERFLOW, DFD_ERR_INBOX_OVERFLOW, DFD_ERR_DEAD_END, DFD_ERR_WRONG_TERMINAL, DFD_ERR_BAD_VC, DFD_ERR_SELF_SEND,
-       DFD_ERR_LATE_EVENT };
+       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR };

@@ -101,6 +101,20 @@ int dfd_engine_finish(dfd_engine* e, void* cuda_stream);
 /* all of tw_run() in one call with host buffers on both sides */
 int dfd_tw_run(dfd_engine* e, void* cuda_stream);
 
+/* Group-sharded run over several GPUs of one box, one process per GPU (the reference's analogue is
+ * codes_mapping()'s block mapping of LPs to MPI ranks, src/util/codes_mapping.c:78-86, with ROSS moving remote
+ * events over MPI).  Rank k owns the dragonfly groups [k*G/world, (k+1)*G/world).  Sequence on every rank:
+ *   set_partition -> engine_upload -> ipc_export -> (all-gather the 64-byte handles) -> ipc_import -> (barrier)
+ *   -> engine_run -> engine_finish -> export_partition -> (gather on rank 0) -> import_partition x (world-1)
+ *   -> engine_finalize (rank 0) -> lp_io_flush / report_stats (rank 0). */
+int dfd_engine_set_partition(dfd_engine* e, int rank, int world);
+int dfd_engine_ipc_export(dfd_engine* e, void* handle64);
+int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world);
+long long dfd_engine_partition_bytes(const dfd_engine* e);
+int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len);
+int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len);
+int dfd_engine_finalize(dfd_engine* e);
+
 /* lp_io_prepare + lp_io_flush (codes/lp-io.h:23-32): writes dragonfly-link-stats, dragonfly-cn-stats,
  * model-net-category-*, synthetic-stats (+ raw-lp-stats with exact hex floats) into `directory` */
 int dfd_lp_io_flush(dfd_engine* e, const char* directory);

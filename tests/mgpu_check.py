@@ -1,0 +1,59 @@
+"""Multi-GPU parity check of the group-sharded engine (run with torchrun, one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+Rank 0 compares the merged lp-io output with the CPU oracle: N-GPU results must be bit-identical to the
+sequential run (the reference's analogue: --sync=1 vs --sync=3 equality, tests/CMakeLists.txt:66-68)."""
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+import codes_b200
+from tests import oracle_util
+
+CASES = [
+    ("configs/dfdally-72.conf", dict(num_messages=20)),
+    ("configs/dfdally-72.conf", dict(num_messages=10, traffic=3)),
+    ("configs/dfdally-1056.conf", dict(num_messages=10)),
+    ("configs/dfdally-8320-par.conf", dict(num_messages=3, traffic=3)),
+]
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl")
+    ok = True
+    for conf, opts in CASES:
+        conf = os.path.join(ROOT, conf)
+        with tempfile.TemporaryDirectory() as tmp:
+            gdir, odir = os.path.join(tmp, "gpu"), os.path.join(tmp, "oracle")
+            t0 = time.perf_counter()
+            s = codes_b200.run_sharded(conf, dist, lp_io_dir=gdir if rank == 0 else None, **opts)
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                o = oracle_util.run(conf, lp_io_dir=odir, **opts)
+                g, r = oracle_util.read_dir(gdir), oracle_util.read_dir(odir)
+                same = s.events == o.events and all(g.get(k) == r[k] for k in r)
+                ok &= same
+                print(f"[{dist.get_world_size()} GPUs] {os.path.basename(conf)} {opts}: events {s.events} vs oracle {o.events}, "
+                      f"windows {s.windows}, {dt:.2f} s -> {'IDENTICAL' if same else 'DIFFERENT'}", flush=True)
+                if not same:
+                    for k in r:
+                        if g.get(k) != r[k]:
+                            print("   differs:", k)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MGPU PARITY OK" if ok else "MGPU PARITY FAIL", flush=True)
+        sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
