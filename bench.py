@@ -119,6 +119,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="N>1: run N independent replicas instead of the group-sharded engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -136,21 +137,37 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl")
 
     w = dict(WORKLOAD)
     conf = w.pop("conf")
     opts = codes_b200.make_opts(**w)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    sharded = world > 1 and not args.replicas
 
     eng = codes_b200.Engine()
     eng.setup(conf, opts)
+    if sharded:  # group-sharded over the ranks: P2P inbox writes + cross-GPU window barrier over NVLink
+        eng.set_partition(rank, world)
     eng.upload(stream)
+    if sharded:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export())
+        eng.ipc_import(handles)
+
+    def fence():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
 
     def one_step(timed):
+        if sharded:
+            fence()  # nobody may reset its sync block while a peer is still closing the last window
         eng.reset(stream)
         flush.fill_(1)  # evict LP state from L2 between steps
+        if sharded:
+            fence()
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -162,58 +179,85 @@ def main():
 
     for _ in range(max(args.warmup, 0)):
         one_step(False)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    fence()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
     evs = [one_step(True) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
+    fence()
     torch.cuda.synchronize()
     clocks = sampler.stop()
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
     eng.finish(stream)
+    if sharded:
+        parts = [None] * world
+        dist.gather_object(eng.export_partition(), parts if rank == 0 else None, dst=0)
+        if rank == 0:
+            for k in range(1, world):
+                eng.import_partition(parts[k])
+            eng.finalize()
     s = eng.summary()
-    events_per_step, packets_per_step = s.events, s.finished_packets
-    hops, chunks, windows = s.total_hops, s.finished_chunks, s.windows
+    meta = [s.events, s.finished_packets, s.total_hops, s.finished_chunks, s.windows] if rank == 0 or not sharded else [0] * 5
+    if sharded:
+        mt = torch.tensor(meta, dtype=torch.int64, device="cuda")
+        dist.broadcast(mt, 0)
+        meta = [int(x) for x in mt]
+    events_per_step, packets_per_step, hops, chunks, windows = meta
 
     # e2e: the reference's main() call sequence, host buffers on both sides, H2D + D2H inside the timed region
-    e2e_eng = codes_b200.Engine()
-    e2e_eng.setup(conf, opts)
-    e2e_eng.tw_run(stream)  # warm (allocations, module load)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_eng.tw_run(stream)
-    e2e_s = time.perf_counter() - t0
-    es = e2e_eng.summary()
-    assert es.events == events_per_step
+    if sharded:
+        codes_b200.run_sharded(conf, dist, stream=stream, **w)  # warm
+        fence()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            es = codes_b200.run_sharded(conf, dist, stream=stream, **w)
+        fence()
+        e2e_s = time.perf_counter() - t0
+        h2d, d2h = (es.h2d_bytes, es.d2h_bytes) if rank == 0 else (0, 0)
+    else:
+        e2e_eng = codes_b200.Engine()
+        e2e_eng.setup(conf, opts)
+        e2e_eng.tw_run(stream)  # warm (allocations, module load)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_eng.tw_run(stream)
+        e2e_s = time.perf_counter() - t0
+        es = e2e_eng.summary()
+        assert es.events == events_per_step
+        h2d, d2h = es.h2d_bytes, es.d2h_bytes
 
     t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     kernel_ms, e2e_s = float(t[0]), float(t[1])
-    total_events = events_per_step * args.steps * world  # N independent replicas of the workload (see config.parallelism)
+    jobs = 1 if (sharded or world == 1) else world  # replicas: N independent simulations
+    total_events = events_per_step * args.steps * jobs
     value = total_events / (kernel_ms * 1e-3)
     peak, peak_src = peaks()
-    ach = algorithmic_bytes(hops, chunks) * args.steps / (kernel_ms * 1e-3) / 1e9
+    ach = algorithmic_bytes(hops, chunks) * args.steps * jobs / (kernel_ms * 1e-3) / 1e9
+    if world == 1:
+        par = "1 GPU"
+    elif sharded:
+        par = f"dragonfly groups sharded over {world} GPUs (one process per GPU): global-link chunks/credits and ACK statistics are " \
+              f"written into the owner GPU's inbox over NVLink P2P, one flag+minimum exchange per lookahead window"
+    else:
+        par = f"{world} independent replicas"
     line = {"metric": "committed events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak",
             "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "events_per_step": events_per_step, "packets_per_step": packets_per_step,
-                       "packets_per_s": packets_per_step * args.steps * world / (kernel_ms * 1e-3),
+                       "packets_per_s": packets_per_step * args.steps * jobs / (kernel_ms * 1e-3),
                        "windows_per_step": windows, "window_ns": s.window_ns, "us_per_window": 1e3 * kernel_ms / args.steps / max(windows, 1),
                        "l2": "256 MiB buffer written between timed steps (L2 flush)",
-                       "grid": [s.grid_blocks, s.block_threads], "device_bytes": s.device_bytes,
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (group-sharded exchange not built yet)"},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step)",
-                         "note": "the kernel is bound by per-window latency (grid barrier + dependent loads), not by HBM bandwidth"},
-            "e2e": {"value": events_per_step * args.steps * world / e2e_s, "unit": "events/s", "h2d_bytes_per_step": es.h2d_bytes,
-                    "d2h_bytes_per_step": es.d2h_bytes, "ms_per_step": 1e3 * e2e_s / args.steps},
+                       "grid": [s.grid_blocks, s.block_threads], "device_bytes": s.device_bytes, "parallelism": par},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * (world if sharded or jobs > 1 else 1), "unit": "GB/s",
+                         "frac": ach / (peak * (world if sharded or jobs > 1 else 1)), "traffic": None,
+                         "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step per GPU)",
+                         "note": "the kernel is bound by per-window latency (grid barrier + dependent instruction chain of the slowest LP), not by HBM bandwidth; see DESIGN.md 5"},
+            "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": 2 * args.steps, "clocks": clocks}
     if rank == 0 and not args.no_cpu_baseline:
         from tests import oracle_util

@@ -94,6 +94,7 @@ ABI = [
     ("dfd_engine_ipc_export", _I, [_P, _P]),
     ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
     ("dfd_engine_partition_bytes", _LL, [_P]),
+    ("dfd_partition_bounds", _I, [_I, _I, _I, _I, _I, ctypes.POINTER(_I)]),
     ("dfd_engine_export_partition", _I, [_P, _P, _LL]),
     ("dfd_engine_import_partition", _I, [_P, _P, _LL]),
     ("dfd_engine_finalize", _I, [_P]),
@@ -130,6 +131,14 @@ def bytes_to_ns(nbytes, gib_per_s):
 
 def cuda_device_count():
     return load_library().dfd_cuda_device_count()
+
+
+def partition_bounds(num_groups, routers_per_group, cns_per_router, rank, world):
+    """(first node, end node, first router, end router) owned by `rank` of `world` (contiguous groups)."""
+    out = (_I * 4)()
+    if load_library().dfd_partition_bounds(num_groups, routers_per_group, cns_per_router, rank, world, out) != 0:
+        raise EngineError(f"bad partition: rank {rank} of {world} over {num_groups} groups")
+    return tuple(out)
 
 
 def make_opts(traffic=UNIFORM, num_messages=20, payload_sz=2048, rperm_threshold=131072, arrival_time=0.0,

@@ -1086,6 +1086,16 @@ struct PartHeader {
     unsigned long long counters[64];
 };
 }
+int dfd_partition_bounds(int num_groups, int routers_per_group, int cns_per_router, int rank, int world, int* out4) {
+    if (world < 1 || world > DFD_MAX_RANKS || rank < 0 || rank >= world || world > num_groups) return 1;
+    DfdPeers X;
+    dfd_partition(num_groups, routers_per_group, cns_per_router, rank, world, &X);
+    out4[0] = X.n0;
+    out4[1] = X.n1;
+    out4[2] = X.r0;
+    out4[3] = X.r1;
+    return 0;
+}
 long long dfd_engine_partition_bytes(const dfd_engine* e) {
     const DfdPeers& X = e->dev.X;
     size_t nn = X.n1 - X.n0, nr = X.r1 - X.r0;

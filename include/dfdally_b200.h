@@ -111,6 +111,8 @@ int dfd_engine_set_partition(dfd_engine* e, int rank, int world);
 int dfd_engine_ipc_export(dfd_engine* e, void* handle64);
 int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world);
 long long dfd_engine_partition_bytes(const dfd_engine* e);
+/* ownership arithmetic: out4 = {first node, end node, first router, end router} of `rank` */
+int dfd_partition_bounds(int num_groups, int routers_per_group, int cns_per_router, int rank, int world, int* out4);
 int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len);
 int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len);
 int dfd_engine_finalize(dfd_engine* e);
