@@ -1,9 +1,11 @@
-"""Regenerates tests/golden/*: outputs of the CPU oracle on the committed configs.
+"""Regenerates tests/golden/*: golden output vectors for the committed configs.
 
-The reference pins no numeric results for this path and cannot be built here (ROSS, MPI,
-flex/bison are absent), so these vectors are produced by oracle/dfdally_oracle.cpp, which restates the
-reference's handlers.  They pin (i) the oracle against accidental change and (ii) the GPU engine on the
-GPU box, where /root/reference does not exist.  Run:  python -m tests.make_golden"""
+The reference pins no numeric results for this path.  The vectors are produced in the authoring
+container by the reference-source oracle -- the reference's OWN sources for this path compiled unchanged against the
+ROSS/MPI shim (oracle/ref -> oracle/_ref) -- and every file is checked to be byte-identical to the output of the
+restatement oracle (oracle/dfdally_oracle.cpp) before it is written.  They pin (i) the restatement against accidental
+change and (ii) the GPU engine on the GPU box, where /root/reference does not exist.
+Run (in the authoring container):  python -m tests.make_golden"""
 import hashlib
 import json
 import os
@@ -22,7 +24,15 @@ def main():
         with tempfile.TemporaryDirectory() as tmp:
             res = oracle_util.run(conf, lp_io_dir=tmp, **case)
             out = oracle_util.read_dir(tmp)
+            if not oracle_util.ref_available() and not oracle_util.build_ref():
+                raise SystemExit("oracle/_ref is needed to generate golden vectors (build it where /root/reference exists)")
+            ev, _, _ = oracle_util.run_ref(conf, os.path.join(tmp, "ref"), **case)
+            ref = oracle_util.read_dir(os.path.join(tmp, "ref"))
+            assert ev == res.events
+            for k in oracle_util.REF_FILES:
+                assert ref[k] == out[k], (name, k)
             meta = dict(conf=os.path.relpath(conf, oracle_util.ROOT), options=case, events=res.events,
+                        generated_by="oracle/_ref (reference sources + ROSS/MPI shim); identical to oracle/dfdally_oracle.cpp",
                         finished_packets=res.finished_packets, total_hops=res.total_hops,
                         sha256={k: hashlib.sha256(v).hexdigest() for k, v in sorted(out.items())})
             with open(os.path.join(GOLDEN, name + ".json"), "w") as f:

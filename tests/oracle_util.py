@@ -90,3 +90,54 @@ def read_dir(d):
             with open(p, "rb") as fh:
                 out[f] = fh.read()
     return out
+
+
+# ---- reference-source oracle: the reference's own sources compiled unchanged against oracle/ref/shim -> oracle/_ref
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "model-net-synthetic-dragonfly-all")
+REF_FILES = ["dragonfly-cn-stats", "dragonfly-link-stats", "model-net-category-all", "model-net-category-test",
+             "synthetic-stats"]
+
+
+def ref_available():
+    return os.path.exists(REF_BIN)
+
+
+def build_ref():
+    """Only possible where /root/reference exists (the authoring container)."""
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ORACLE_DIR, "ref")], check=True)
+    return ref_available()
+
+
+def run_ref(conf, lp_io_dir, traffic=1, num_messages=20, payload_sz=2048, arrival_time=0.0, load_per_svr=0.0,
+            warm_up_time=0.0, end_time=0.0):
+    """Run the reference binary twin (sequential shim engine). Returns (events, event-loop seconds, stdout)."""
+    import re
+    import shutil
+    conf = os.path.abspath(conf)
+    shutil.rmtree(lp_io_dir, ignore_errors=True)  # lp_io_prepare refuses an existing directory
+    args = [REF_BIN, "--sync=1", f"--traffic={traffic}", f"--num_messages={num_messages}", f"--payload_sz={payload_sz}"]
+    if arrival_time:
+        args.append(f"--arrival_time={arrival_time}")
+    if load_per_svr:
+        args.append(f"--load_per_svr={load_per_svr}")
+    if warm_up_time:
+        args.append(f"--warm_up_time={warm_up_time}")
+    if end_time:
+        args.append(f"--end={end_time}")
+    args += [f"--lp-io-dir={os.path.abspath(lp_io_dir)}", "--", conf]
+    r = subprocess.run(args, cwd=os.path.dirname(conf), capture_output=True, text=True)  # link files are cwd-relative
+    if r.returncode != 0:
+        raise OracleError("reference-source oracle failed: " + r.stderr[-500:])
+    ev = int(re.search(r"Net Events Processed\s+(\d+)", r.stdout).group(1))
+    m = re.search(r"shim: (\d+) events in ([0-9.]+) s", r.stderr)
+    return ev, float(m.group(2)), r.stdout
+
+
+def stdout_stats_block(text):
+    """The statistics the driver prints after the run (dally:3169-3190, synthetic:635-657), without blank lines."""
+    lines = text.splitlines()
+    for i, l in enumerate(lines):
+        if l.startswith("Average number of hops"):
+            return [x for x in lines[i:] if x.strip()]
+    return []

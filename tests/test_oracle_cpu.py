@@ -193,3 +193,87 @@ def test_oracle_matches_golden(tmp_path, name):
 def test_config_errors():
     with pytest.raises(oracle_util.OracleError):
         oracle_util.run("/nonexistent.conf")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pinning the restatement: the reference's OWN handler sources (compiled unchanged against the ROSS/MPI shim,
+# oracle/ref/) must produce byte-identical lp-io files, the same `Net Events Processed` and the same stdout statistics.
+# ------------------------------------------------------------------------------------------------------------------
+REF_CASES = [
+    ("72-m1", CONF72, dict(num_messages=1)),
+    ("72-m20", CONF72, dict(num_messages=20)),
+    ("72-nearest-group", CONF72, dict(num_messages=10, traffic=3)),
+    ("72-rand-perm", CONF72, dict(num_messages=10, traffic=2)),
+    ("72-nearest-neighbor", CONF72, dict(num_messages=10, traffic=4)),
+    ("72-random-other-group", CONF72, dict(num_messages=5, traffic=5)),
+    ("72-high-load", CONF72, dict(num_messages=30, arrival_time=200.0)),
+    ("72-load-per-svr", CONF72, dict(num_messages=10, load_per_svr=0.5)),
+    ("72-small-payload", CONF72, dict(num_messages=10, payload_sz=8)),
+    ("72-full-chunk", CONF72, dict(num_messages=10, payload_sz=4096)),
+    ("72-warmup", CONF72, dict(num_messages=10, warm_up_time=3000.0)),
+    ("72-end-time", CONF72, dict(num_messages=20, end_time=12000.0)),
+    ("1056-uniform", CONF1056, dict(num_messages=5)),
+    ("8320-par-nearest-group", CONF8K, dict(num_messages=2, traffic=3)),
+]
+
+
+@pytest.fixture(scope="session")
+def ref_oracle():
+    if not oracle_util.ref_available() and not oracle_util.build_ref():
+        pytest.skip("oracle/_ref is not built (needs /root/reference)")
+    return oracle_util
+
+
+@pytest.mark.parametrize("name,conf,opts", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_restatement_matches_reference_sources(tmp_path, ref_oracle, name, conf, opts):
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
+    ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
+    res = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert ev == res.events
+    r, o = oracle_util.read_dir(rdir), oracle_util.read_dir(odir)
+    for f in oracle_util.REF_FILES:
+        assert r.get(f) == o.get(f), f
+    assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
+
+
+def ref_variant(tmp_path, base, **params):
+    import re
+    with open(base) as f:
+        text = f.read()
+    d, stem = os.path.dirname(base), os.path.basename(base)[:-5]
+    text = text.replace(f'"{stem}-intra"', f'"{d}/{stem}-intra"').replace(f'"{stem}-inter"', f'"{d}/{stem}-inter"')
+    for k, v in params.items():
+        if re.search(r'^\s*' + re.escape(k) + r'\s*=', text, flags=re.M):
+            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}="{v}";', text, flags=re.M)
+        else:
+            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}="{v}";')
+    p = tmp_path / "variant.conf"
+    p.write_text(text)
+    return str(p)
+
+
+REF_VARIANTS = [
+    ("72-nonminimal", CONF72, dict(routing="nonminimal"), dict(num_messages=10)),
+    ("72-par", CONF72, dict(routing="prog-adaptive", adaptive_threshold="0"), dict(num_messages=20, traffic=3)),
+    ("72-par-alpha", CONF72, dict(routing="prog-adaptive", route_scoring_metric="alpha"), dict(num_messages=20, arrival_time=300.0)),
+    ("72-credit-delay-100", CONF72, dict(credit_delay="100"), dict(num_messages=20)),
+    ("72-tiny-vcs", CONF72, dict(local_vc_size="4096", global_vc_size="4096", cn_vc_size="4096"), dict(num_messages=10)),
+    ("72-asym-bw", CONF72, dict(local_bandwidth="5.25", global_bandwidth="4.7", cn_bandwidth="8.0", router_delay="50"), dict(num_messages=10)),
+    ("72-multichunk", CONF72, dict(chunk_size="1024"), dict(num_messages=10)),                 # packets of 2 chunks
+    ("72-multipacket", CONF72, dict(packet_size="1024", chunk_size="1024"), dict(num_messages=10)),  # messages of 2 packets
+    ("72-multi-both", CONF72, dict(packet_size="2048", chunk_size="512"), dict(num_messages=6, payload_sz=5000)),
+    ("1056-par", CONF1056, dict(routing="prog-adaptive", adaptive_threshold="16384"), dict(num_messages=4, traffic=3)),
+]
+
+
+@pytest.mark.parametrize("name,base,params,opts", REF_VARIANTS, ids=[v[0] for v in REF_VARIANTS])
+def test_restatement_matches_reference_sources_config_variants(tmp_path, ref_oracle, name, base, params, opts):
+    conf = ref_variant(tmp_path, base, **params)
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
+    ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
+    res = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert ev == res.events
+    r, o = oracle_util.read_dir(rdir), oracle_util.read_dir(odir)
+    for f in oracle_util.REF_FILES:
+        assert r.get(f) == o.get(f), f
+    assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
