@@ -587,8 +587,8 @@ __device__ __forceinline__ void term_buf_update(Ctx& c, unsigned n, NodeState* s
     }
 }
 
-// packet_arrive dally:6453-6744 (single-chunk packets, single-packet messages: the reassembly entry is
-// created and retired inside this one call)
+// packet_arrive dally:6453-6744.  Packets of one chunk that are a whole message (the BASELINE workloads) never touch
+// the reassembly tables: their rank_tbl entry would be created and retired inside this one call.
 __device__ void term_packet_arrive(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const ChunkRec& m) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
@@ -616,11 +616,60 @@ __device__ void term_packet_arrive(Ctx& c, unsigned n, NodeState* s, NodeEv* lis
     }
     if (s->min_latency > ete_latency) s->min_latency = ete_latency;
     if (s->max_latency < ete_latency) s->max_latency = ete_latency;
-    // packet complete (chunk_size >= packet_size) and message complete (one packet)
-    s->total_msg_size += m.total_size;
-    s->finished_msgs++;
-    if (m.flags & 1u)  // send_remote_event dally:6124-6151: REMOTE to the destination svr at +0
-        node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_REMOTE, m.src_svr, 0, 0, m.msg_start_time);
+    bool message_done;
+    bool has_remote = (m.flags & 1u) != 0;
+    if (m.packet_size <= (unsigned)P.chunk_size && m.total_size <= (unsigned)P.packet_size) {
+        message_done = true;  // one chunk == one packet == the whole message
+    } else {
+        // remaining_sz_packets (dally:6590-6618): bytes still missing of a multi-chunk packet
+        bool packet_done = false;
+        uint4* pt = &A.ptab[(size_t)n * P.nreasm_cap];
+        unsigned pi = 0;
+        for (; pi < s->pt_n; pi++)
+            if (pt[pi].x == m.packet_id && pt[pi].y == m.src_term) break;
+        if (pi < s->pt_n) {
+            unsigned actual = min((unsigned)P.chunk_size, pt[pi].z);
+            pt[pi].z -= actual;
+            if (pt[pi].z == 0) {
+                packet_done = true;
+                pt[pi] = pt[--s->pt_n];
+            }
+        } else if ((unsigned)P.chunk_size < m.packet_size) {
+            if (s->pt_n >= (unsigned)P.nreasm_cap) {
+                set_error(A, DFD_ERR_REASM_OVERFLOW, n);
+                return;
+            }
+            pt[s->pt_n++] = make_uint4(m.packet_id, m.src_term, m.packet_size - P.chunk_size, 0);
+        } else
+            packet_done = true;
+        // rank_tbl (dally:6620-6720): packets still missing of the message, keyed by (message_id, sender)
+        uint4* mt = &A.mtab[(size_t)n * P.nreasm_cap];
+        unsigned mi = 0;
+        for (; mi < s->mt_n; mi++)
+            if (mt[mi].x == m.message_id && mt[mi].y == m.src_svr) break;
+        if (mi == s->mt_n) {
+            if (s->mt_n >= (unsigned)P.nreasm_cap) {
+                set_error(A, DFD_ERR_REASM_OVERFLOW, n);
+                return;
+            }
+            unsigned total_packets = m.total_size / (unsigned)P.packet_size + (m.total_size % (unsigned)P.packet_size ? 1 : 0);
+            if (total_packets == 0) total_packets = 1;
+            mt[s->mt_n++] = make_uint4(m.message_id, m.src_svr, total_packets, 0);
+        }
+        if (has_remote) mt[mi].w = 1;  // the last packet's chunks carry the remote event
+        if (packet_done) mt[mi].z--;
+        message_done = mt[mi].z == 0;
+        if (message_done) {
+            has_remote = mt[mi].w != 0;
+            mt[mi] = mt[--s->mt_n];
+        }
+    }
+    if (message_done) {
+        s->total_msg_size += m.total_size;
+        s->finished_msgs++;
+        if (has_remote)  // send_remote_event dally:6124-6151: REMOTE to the destination svr at +0
+            node_add_event(c, n, s, list, now + 0.0, tg, s->term_seq++, EV_REMOTE, m.src_svr, 0, 0, m.msg_start_time);
+    }
 }
 
 __device__ void node_process(Ctx& c, unsigned n) {
@@ -1851,6 +1900,8 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.tq, NT * P.ntq_cap)) return 1;
     if (dalloc(dev, &A.ncin, NT * P.ncin_cap)) return 1;
     if (dalloc(dev, &A.nkin, NT * P.nkin_cap)) return 1;
+    if (dalloc(dev, &A.mtab, NT * (size_t)P.nreasm_cap)) return 1;
+    if (dalloc(dev, &A.ptab, NT * (size_t)P.nreasm_cap)) return 1;
     if (dalloc(dev, &A.ncin_tail, NT)) return 1;
     if (dalloc(dev, &A.nkin_tail, NT)) return 1;
     if (dalloc(dev, &A.rh, NR)) return 1;

@@ -640,6 +640,9 @@ const char* device_error_name(unsigned long long code) {
     case DFD_ERR_BAD_VC: return "Output channel greater than available VCs";
     case DFD_ERR_SELF_SEND: return "self-addressed network message above the eager limit";
     case DFD_ERR_LATE_EVENT: return "event scheduled inside the current window";
+    case DFD_ERR_PEER_TIMEOUT: return "a peer GPU did not reach the window barrier";
+    case DFD_ERR_PEER_ERROR: return "a peer GPU reported an error";
+    case DFD_ERR_REASM_OVERFLOW: return "too many messages being reassembled at one terminal (raise DFD_REASM_CAP)";
     }
     return "unknown";
 }
@@ -815,9 +818,9 @@ int dfd_synthetic_configure(dfd_engine* e, const dfd_synthetic_opts* o) {
     const HostParams& p = e->hp;
     if (o->traffic < 1 || o->traffic > 5) return fail(e, "unknown traffic pattern %d", o->traffic);
     if (o->payload_sz <= 0) return fail(e, "payload_sz must be positive");
-    if ((unsigned long long)o->payload_sz > p.mn_packet_size || o->payload_sz > p.chunk_size)
-        return fail(e, "this engine handles single-chunk, single-packet messages: payload_sz (%d) must not exceed packet_size (%llu) and chunk_size (%d) (SURVEY 8f-1)",
-                    o->payload_sz, p.mn_packet_size, p.chunk_size);
+    if (p.packet_size <= 0) return fail(e, "packet_size must be set (the reference's fallback for a missing packet_size is not supported)");
+    if ((unsigned long long)o->payload_sz > 0xFFFFFFFFull || (p.mn_packet_size + p.chunk_size - 1) / p.chunk_size > 65535)
+        return fail(e, "message / packet too large for the packed chunk record");
     if (72 + 72 + 416 > p.message_size)  // model-net.c:294-300
         return fail(e, "Error: model_net trying to transmit an event of size %d but ROSS is configured for events of size %d\n", 560, p.message_size);
     // issue_event synthetic:243-254
@@ -919,7 +922,14 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->ncin_cap = next_pow2(DFD_NUM_VCS * cn_chunks + 1);
     P->nkin_cap = next_pow2(cn_chunks + 1);
     P->nsq_cap = next_pow2(std::max(2, o.num_messages + 1));
-    P->ntq_cap = next_pow2(cn_chunks + 2);
+    int chunks_per_packet = (int)((std::min<unsigned long long>(p.mn_packet_size, (unsigned long long)o.payload_sz) + p.chunk_size - 1) / p.chunk_size);
+    if (chunks_per_packet < 1) chunks_per_packet = 1;
+    P->ntq_cap = next_pow2(cn_chunks + chunks_per_packet + 2);
+    // reassembly tables are only needed when a message is more than one chunk; 4999 is the reference's own limit on
+    // concurrently reassembled messages per terminal (DFLY_HASH_TABLE_SIZE, dally:68, :6676-6678)
+    bool multi = (unsigned long long)o.payload_sz > p.mn_packet_size || o.payload_sz > p.chunk_size;
+    P->nreasm_cap = multi ? 256 : 0;
+    if (const char* ev = getenv("DFD_REASM_CAP")) if (multi) P->nreasm_cap = std::max(4, std::min(4999, atoi(ev)));
     P->nev_cap = 24;
     // in-degree per router type equals out-degree for the link files we accept (checked below)
     long long in_chunks = (long long)p.intra_grp_radix * DFD_NUM_VCS * loc_chunks + (long long)p.global_radix * DFD_NUM_VCS * glb_chunks + (long long)p.num_cn * cn_chunks;

@@ -2,6 +2,7 @@
 // Terminology follows the reference (terminal, router, chunk, credit, VC, port).
 #pragma once
 #include <stdint.h>
+#include <vector_types.h>
 
 #define DFD_NUM_VCS 4  // dragonfly-dally.cxx:2387 (num_qos_levels == 1)
 
@@ -217,7 +218,8 @@ struct __attribute__((aligned(16))) NodeState {
     unsigned long long rng_draws;
     // global counters contributed by this node (packet_generate dally:5601-5615, packet_arrive :6512-6522)
     uint32_t local_sr, local_sg, remote_pk, minimal_count, nonmin_count, pad2;
-    uint32_t svr_gid, term_gid, pad3, pad4;
+    uint32_t svr_gid, term_gid;
+    uint32_t mt_n, pt_n;  // live entries of the message / packet reassembly tables
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)
@@ -246,6 +248,7 @@ struct DfdParams {
     int lps_per_rep, off_svr, off_term, off_rtr;
     // ring capacities (powers of two) and heap/pool capacities
     int ncin_cap, nkin_cap, nsq_cap, ntq_cap, nev_cap;
+    int nreasm_cap;  // per-terminal reassembly table entries (0: every message is one chunk)
     int rcin_cap, rkin_cap, rpool_cap, rheap_cap;
 };
 
@@ -262,6 +265,8 @@ struct DfdArrays {
     TermChunk* tq;          // [NT][ntq_cap]
     ChunkRec* ncin;         // [NT][ncin_cap]
     CreditRec* nkin;        // [NT][nkin_cap]
+    uint4* mtab;            // [NT][nreasm_cap] rank_tbl: {message_id, sender svr, remaining_packets, has_remote}
+    uint4* ptab;            // [NT][nreasm_cap] remaining_sz_packets: {packet_id, source terminal, remaining bytes, -}
     unsigned* ncin_tail;    // [NT]
     unsigned* nkin_tail;    // [NT]
     unsigned* ack_count;             // [NT]
@@ -314,4 +319,4 @@ struct DfdPeers {
 
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,
        DFD_ERR_HEAP_OVERFLOW, DFD_ERR_INBOX_OVERFLOW, DFD_ERR_DEAD_END, DFD_ERR_WRONG_TERMINAL, DFD_ERR_BAD_VC, DFD_ERR_SELF_SEND,
-       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR };
+       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR, DFD_ERR_REASM_OVERFLOW };

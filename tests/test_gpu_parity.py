@@ -86,6 +86,11 @@ VARIANTS = [
     ("72-credit-delay-100", CONF72, dict(credit_delay="100"), dict(num_messages=20)),  # wider lookahead window
     ("72-tiny-vcs", CONF72, dict(local_vc_size="4096", global_vc_size="4096", cn_vc_size="4096"), dict(num_messages=10)),
     ("72-asym-bw", CONF72, dict(local_bandwidth="5.25", global_bandwidth="4.7", cn_bandwidth="8.0", router_delay="50"), dict(num_messages=10)),
+    ("72-multichunk", CONF72, dict(chunk_size="1024"), dict(num_messages=10)),                       # packets of 2 chunks
+    ("72-multipacket", CONF72, dict(packet_size="1024", chunk_size="1024"), dict(num_messages=10)),  # messages of 2 packets
+    ("72-multi-both", CONF72, dict(packet_size="2048", chunk_size="512"), dict(num_messages=6, payload_sz=5000)),
+    ("72-multi-par", CONF72, dict(packet_size="2048", chunk_size="512", routing="prog-adaptive"), dict(num_messages=8, payload_sz=6000, traffic=3)),
+    ("72-big-payload", CONF72, dict(), dict(num_messages=5, payload_sz=20000)),                        # 5 packets per message
     ("1056-nonminimal", CONF1056, dict(routing="nonminimal"), dict(num_messages=4)),
     ("1056-par", CONF1056, dict(routing="prog-adaptive", adaptive_threshold="16384"), dict(num_messages=6, traffic=3)),
 ]

@@ -114,8 +114,7 @@ def test_defaults_follow_reference(engine_lib, tmp_path):
     # explicit credit_delay and missing optional keys are accepted (dally:2663-2756)
     configure(write_conf(tmp_path, credit_delay="100"), num_messages=1)
     configure(write_conf(tmp_path, routing=None), num_messages=1)  # default: minimal (dally:2300-2305)
-    with pytest.raises(codes_b200.EngineError, match="single-chunk"):
-        configure(CONF72, num_messages=1, payload_sz=8192)
+    configure(CONF72, num_messages=1, payload_sz=8192)  # multi-packet messages are accepted
     with pytest.raises(codes_b200.EngineError, match="unknown traffic"):
         configure(CONF72, traffic=9)
 
