@@ -76,6 +76,15 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the window kernel for this workload, from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    return None
+
+
 def algorithmic_bytes(total_hops, chunks):
     return 832 * total_hops + 896 * chunks  # SURVEY 8(d)
 
@@ -268,7 +277,8 @@ def main():
                        "l2": "256 MiB buffer written between timed steps (L2 flush)",
                        "grid": [s.grid_blocks, s.block_threads], "device_bytes": s.device_bytes, "parallelism": par},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * (world if sharded or jobs > 1 else 1), "unit": "GB/s",
-                         "frac": ach / (peak * (world if sharded or jobs > 1 else 1)), "traffic": None,
+                         "frac": ach / (peak * (world if sharded or jobs > 1 else 1)), "traffic": measured_traffic() if world == 1 else None,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(hops, chunks),
                          "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step per GPU)",
                          "note": "the kernel is bound by per-window latency (grid barrier + dependent instruction chain of the slowest LP), not by HBM bandwidth; see DESIGN.md 5"},
             "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
