@@ -1595,7 +1595,7 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
     extern __shared__ unsigned s_list[];  // [lps_per_block]: bit31 = router, low bits = index; then tc/tk halves
     __shared__ double s_min[DFD_BLOCK / 32];
     __shared__ unsigned s_ev[EV_NTYPES];
-    __shared__ unsigned s_n;
+    __shared__ unsigned s_n, s_nr;  // active nodes (list front) / active routers (list back)
     const unsigned tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
     // this rank owns nodes [X.n0, X.n1) and routers [X.r0, X.r1); the block takes a contiguous slice of each
     const unsigned ntb = ((unsigned)(X.n1 - X.n0) + gridDim.x - 1) / gridDim.x, nrb = ((unsigned)(X.r1 - X.r0) + gridDim.x - 1) / gridDim.x;
@@ -1608,8 +1608,12 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
     c.X = &X;
     c.ev = s_ev;
     if (tid < EV_NTYPES) s_ev[tid] = 0;
-    if (tid == 0) s_n = 0;
+    if (tid == 0) {
+        s_n = 0;
+        s_nr = 0;
+    }
     __syncthreads();
+    const unsigned lcap = ntb + nrb;
     unsigned long long w = __ldcg(&A.counters[1]);  // windows executed so far (the kernel may be re-entered)
     const unsigned long long w_stop = w + max_windows;
     const unsigned long long bar0 = __ldcg(&A.counters[28]);  // barrier count at entry
@@ -1680,23 +1684,23 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
                 tk = __ldcg(&A.rkin_tail[(size_t)cur * P.NR + r]);
             }
             if (tc | tk | (unsigned)(ws < te_bits)) {
-                unsigned pos = atomicAdd(&s_n, 1u);
-                s_list[pos] = 0x80000000u | r;
+                unsigned pos = lcap - 1 - atomicAdd(&s_nr, 1u);
+                s_list[pos] = r;
                 s_tails[pos] = (tc << 16) | (tk & 0xFFFFu);
             } else
                 c.cand = fmin(c.cand, bits2d(ws));
         }
         __syncthreads();
         long long c1 = clock64();
-        // (2) process, warp-first distribution
-        const unsigned nact = s_n;
-        for (unsigned j = (tid & 31) * nwarps + (tid >> 5); j < nact; j += nth) {
-            unsigned e = s_list[j];
-            if (e & 0x80000000u) {
-                unsigned t = s_tails[j];
-                router_process(c, e & 0x7FFFFFFFu, t >> 16, t & 0xFFFFu);
-            } else
-                node_process(c, e);
+        // (2) process.  Nodes and routers are dealt out separately so that the lanes of a warp run the same kind of
+        // LP: nodes warp-first from warp 0 upwards, routers warp-first from the last warp downwards (with few active
+        // LPs the two kinds do not share a warp, and no LP shares one with another).
+        const unsigned nact = s_n, ract = s_nr;
+        for (unsigned j = (tid & 31) * nwarps + (tid >> 5); j < nact; j += nth) node_process(c, s_list[j]);
+        for (unsigned j = (tid & 31) * nwarps + (nwarps - 1 - (tid >> 5)); j < ract; j += nth) {
+            unsigned pos = lcap - 1 - j;
+            unsigned t = s_tails[pos];
+            router_process(c, s_list[pos], t >> 16, t & 0xFFFFu);
         }
         if (c.remote_writes) __threadfence_system();  // records written over NVLink must be visible before the flags
         // (3) block-min of the candidates, one atomicMin per block
@@ -1709,6 +1713,7 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
             for (unsigned i = 1; i < nwarps; i++) m = fmin(m, s_min[i]);
             if (d2bits(m) != INF_BITS) atomicMin(&A.gmin[(w + 1) % 3], d2bits(m));
             s_n = 0;
+            s_nr = 0;
         }
         // (4) close the window
         long long c2 = clock64();
