@@ -39,6 +39,7 @@ struct Ctx {
     const DfdParams* P;
     const DfdArrays* A;
     double t_end;
+    long long b_beg;  // timing-wheel bucket of the window start
     double cand;  // min timestamp of everything this thread left pending or pushed this window
     const DfdPeers* X;
     int cur, nxt;
@@ -792,145 +793,100 @@ struct RCtx {
     PortState* port;
     PortQ* pq;
     PoolSlot* pool;
-    double* pts;       // far pending list: timestamps
-    RPendMeta* pmeta;  // far pending list: keys / payload references
-    double* nts;       // near pending list
-    RPendMeta* nmeta;
-    double near_limit; // entries with ts below this go to the near list
+    PendEnt* pent;              // wheel entries
+    unsigned* wheel;            // bucket heads
+    unsigned long long* wbits;  // non-empty-bucket bitmap
+    long long b_beg;            // absolute bucket index of the window start
 };
 
-// Pending events of a router: a small "near" list (everything due before near_limit = window end + a few
-// windows) and a "far" list whose exact minimum is cached in the header.  The far list is only scanned when
-// its minimum drops below near_limit; the near list is what the event loop searches.
+// Pending events of a router: timing wheel, bucket width = one lookahead window (see PendEnt).
+__device__ __forceinline__ long long wheel_bucket(const DfdParams& P, double ts) { return (long long)(ts * P.inv_window); }
+
 __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
-    if (ts >= c.P->ts_end) return;
-    RPendMeta me;
-    me.src = src;
-    me.seq = seq;
-    me.ref = ref;
-    me.pad = 0;
-    if (ts < R.near_limit) {
-        unsigned n = R.h->near_n;
-        if (n >= (unsigned)c.P->rheap_cap) {
-            set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
-            return;
-        }
-        R.nts[n] = ts;
-        *(uint4*)&R.nmeta[n] = *(uint4*)&me;
-        R.h->near_n = n + 1;
-    } else {
-        unsigned n = R.h->far_n;
-        if (n >= (unsigned)c.P->rheap_cap) {
-            set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
-            return;
-        }
-        R.pts[n] = ts;
-        *(uint4*)&R.pmeta[n] = *(uint4*)&me;
-        R.h->far_n = n + 1;
-        if (ts < R.h->far_min) R.h->far_min = ts;
-        if (n + 1 > R.h->heap_hwm) R.h->heap_hwm = n + 1;
+    const DfdParams& P = *c.P;
+    if (ts >= P.ts_end) return;
+    unsigned e = R.h->pent_free;
+    long long b = wheel_bucket(P, ts);
+    if (e == NIL || b - R.b_beg >= (long long)P.wheel_nb || b < R.b_beg) {
+        set_error(*c.A, e == NIL ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE, R.r);
+        return;
     }
+    PendEnt* pe = &R.pent[e];
+    R.h->pent_free = pe->next;
+    unsigned bi = (unsigned)b & (unsigned)(P.wheel_nb - 1);
+    unsigned head = R.wheel[bi];
+    pe->ts = ts;
+    pe->src = src;
+    pe->seq = seq;
+    pe->ref = ref;
+    pe->next = head;
+    R.wheel[bi] = e;
+    if (head == NIL) R.wbits[bi >> 6] |= 1ULL << (bi & 63);
+    unsigned n = ++R.h->pend_n;
+    if (n > R.h->heap_hwm) R.h->heap_hwm = n;
 }
-// move every far entry that is due before near_limit to the near list and recompute the far minimum; the
-// timestamps are fetched eight at a time so that the loads overlap
-__device__ void rpend_refill(Ctx& c, RCtx& R) {
-    unsigned n = R.h->far_n;
-    double* t = R.pts;
-    double fmin_ = DINF;
-    unsigned i = 0;
-    const double lim = R.near_limit;
-    while (i < n) {
-        double v[8];
-        unsigned cnt = min(8u, n - i);
-        if (cnt == 8) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                double2 d = *(const double2*)&t[i + 2 * k];
-                v[2 * k] = d.x;
-                v[2 * k + 1] = d.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = (unsigned)k < cnt ? t[i + k] : DINF;
-        }
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < 8; k++) any |= v[k] < lim;
-        if (!any) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) fmin_ = fmin(fmin_, v[k]);
-            i += cnt;
-            continue;
-        }
-        // slow path for this batch: move due entries out one by one (the hole is filled from the end, and the
-        // entry that lands in it is examined next)
-        unsigned j = i;
-        while (j < i + cnt && j < n) {
-            double tv = t[j];
-            if (tv < lim) {
-                unsigned m = R.h->near_n;
-                if (m >= (unsigned)c.P->rheap_cap) {
-                    set_error(*c.A, DFD_ERR_HEAP_OVERFLOW, R.r);
-                    return;
-                }
-                R.nts[m] = tv;
-                *(uint4*)&R.nmeta[m] = *(const uint4*)&R.pmeta[j];
-                R.h->near_n = m + 1;
-                n--;
-                if (j != n) {
-                    t[j] = t[n];
-                    *(uint4*)&R.pmeta[j] = *(const uint4*)&R.pmeta[n];
-                }
-            } else {
-                fmin_ = fmin(fmin_, tv);
-                j++;
-            }
-        }
-        i = j;
-    }
-    R.h->far_n = n;
-    R.h->far_min = fmin_;
-}
-// index of the earliest near entry by (ts, src, seq); n must be > 0
-__device__ __forceinline__ unsigned rnear_min(const RCtx& R, unsigned n, double* ts_out) {
-    const double* t = R.nts;
-    double best = t[0];
-    unsigned bi = 0;
-    bool tie = false;
-    for (unsigned i = 1; i < n; i++) {
-        double v = t[i];
-        if (v < best) {
-            best = v;
-            bi = i;
-            tie = false;
-        } else if (v == best)
-            tie = true;
-    }
-    if (tie) {  // rare: equal timestamps -> order by (sender gid, sender sequence)
-        unsigned bsrc = 0, bseq = 0;
-        bool first = true;
-        for (unsigned k = 0; k < n; k++) {
-            if (t[k] != best) continue;
-            RPendMeta m = R.nmeta[k];
-            if (first || m.src < bsrc || (m.src == bsrc && m.seq < bseq)) {
-                bi = k;
-                bsrc = m.src;
-                bseq = m.seq;
-                first = false;
+
+// earliest pending event with ts < t_end, by (ts, src, seq), searched in the buckets the window overlaps; unlinks
+// it and returns its payload reference (or 0 when nothing is due)
+__device__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
+    const DfdParams& P = *c.P;
+    const unsigned mask = (unsigned)(P.wheel_nb - 1);
+    const long long b_end = wheel_bucket(P, c.t_end);
+    unsigned best = NIL, best_prev = NIL, best_b = 0;
+    double bts = 0.0;
+    unsigned bsrc = 0, bseq = 0;
+    for (long long b = R.b_beg; b <= b_end; b++) {
+        unsigned bi = (unsigned)b & mask;
+        unsigned prev = NIL;
+        for (unsigned e = R.wheel[bi]; e != NIL; prev = e, e = R.pent[e].next) {
+            const PendEnt& pe = R.pent[e];
+            if (!(pe.ts < c.t_end)) continue;
+            if (best == NIL || key_less(pe.ts, pe.src, pe.seq, bts, bsrc, bseq)) {
+                best = e;
+                best_prev = prev;
+                best_b = bi;
+                bts = pe.ts;
+                bsrc = pe.src;
+                bseq = pe.seq;
             }
         }
     }
-    *ts_out = best;
-    return bi;
-}
-__device__ __forceinline__ unsigned rnear_take(RCtx& R, unsigned idx) {  // remove near entry idx, return its payload reference
-    unsigned ref = R.nmeta[idx].ref;
-    unsigned n = --R.h->near_n;
-    if (idx != n) {
-        R.nts[idx] = R.nts[n];
-        *(uint4*)&R.nmeta[idx] = *(const uint4*)&R.nmeta[n];
-    }
+    if (best == NIL) return 0;
+    PendEnt* pe = &R.pent[best];
+    unsigned nxt = pe->next, ref = pe->ref;
+    if (best_prev == NIL) {
+        R.wheel[best_b] = nxt;
+        if (nxt == NIL) R.wbits[best_b >> 6] &= ~(1ULL << (best_b & 63));
+    } else
+        R.pent[best_prev].next = nxt;
+    pe->next = R.h->pent_free;
+    R.h->pent_free = best;
+    R.h->pend_n--;
+    *now_out = bts;
     return ref;
+}
+
+// exact timestamp of the earliest pending event: the minimum of the first non-empty bucket at or after the window
+// start (bucket index is monotone in the timestamp, so no later bucket can hold an earlier event)
+__device__ double rwheel_next_ts(Ctx& c, RCtx& R) {
+    const DfdParams& P = *c.P;
+    if (R.h->pend_n == 0) return DINF;
+    const unsigned nb = (unsigned)P.wheel_nb, mask = nb - 1, nwords = nb >> 6;
+    unsigned start = (unsigned)R.b_beg & mask;
+    unsigned w = start >> 6;
+    unsigned long long bits = R.wbits[w] & (~0ULL << (start & 63));
+    for (unsigned k = 0; k <= nwords; k++) {
+        if (bits) {
+            unsigned bi = (w << 6) + (unsigned)__ffsll((long long)bits) - 1;
+            double m = DINF;
+            for (unsigned e = R.wheel[bi]; e != NIL; e = R.pent[e].next) m = fmin(m, R.pent[e].ts);
+            return m;
+        }
+        w = (w + 1) & (nwords - 1);
+        bits = R.wbits[w];
+        if (k + 1 == nwords) bits &= ~(~0ULL << (start & 63));  // wrapped around to the first word: the part before start
+    }
+    return DINF;
 }
 
 // --- connection queries (DragonflyConnectionManager, dragonfly-network-manager.cxx) ----------------
@@ -1432,11 +1388,10 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     R.port = &A.port[(size_t)r * P.radix];
     R.pq = &A.portq[(size_t)r * P.radix];
     R.pool = &A.pool[(size_t)r * P.rpool_cap];
-    R.pts = &A.rts[(size_t)r * P.rheap_cap];
-    R.pmeta = &A.rmeta[(size_t)r * P.rheap_cap];
-    R.nts = &A.nts[(size_t)r * P.rheap_cap];
-    R.nmeta = &A.nmeta[(size_t)r * P.rheap_cap];
-    R.near_limit = c.t_end + 4.0 * P.window;
+    R.pent = &A.pent[(size_t)r * P.rheap_cap];
+    R.wheel = &A.wheel[(size_t)r * P.wheel_nb];
+    R.wbits = &A.wbits[(size_t)r * (P.wheel_nb >> 6)];
+    R.b_beg = c.b_beg;
     // drain the inbox filled during the previous window: chunks go to pool slots, keys to the heap
 #ifdef DFD_PROFILE
     long long pd0 = clock64();
@@ -1480,18 +1435,11 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
 #ifdef DFD_PROFILE
     unsigned prof_nev = 0;
 #endif
-    if (R.h->far_min < R.near_limit) rpend_refill(c, R);
-    double next_ts = DINF;
     for (;;) {
-        unsigned np = R.h->near_n;
-        if (np == 0) break;
+        if (R.h->pend_n == 0) break;
         double now;
-        unsigned idx = rnear_min(R, np, &now);
-        if (!(now < c.t_end)) {
-            next_ts = now;
-            break;
-        }
-        unsigned ref = rnear_take(R, idx);
+        unsigned ref = rwheel_pop_due(c, R, &now);
+        if (ref == 0) break;
 #ifdef DFD_PROFILE
         prof_nev++;
 #endif
@@ -1511,7 +1459,7 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
             PROF_ADD(c, EV_R_SEND);
         }
     }
-    next_ts = fmin(next_ts, R.h->far_min);
+    double next_ts = rwheel_next_ts(c, R);
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
 #ifdef DFD_PROFILE
@@ -1642,6 +1590,7 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
         double T = bits2d(tb);
         if (T >= P.ts_end) break;
         c.t_end = T + P.window;
+        c.b_beg = (long long)(T * P.inv_window);
         c.cur = cur;
         c.nxt = cur ^ 1;
         c.widx = (unsigned)w;
@@ -1811,7 +1760,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         memset(h, 0, sizeof(RouterHdr));
         seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
         h->pool_free = 0;
-        h->far_min = bits2d(INF_BITS);
+        h->pent_free = 0;
         h->gid = rtr_gid(P, r);
         h->lid = (uint16_t)(r % P.a);
         h->grp = (uint16_t)(r / P.a);
@@ -1829,6 +1778,14 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         PortQ* pq = &A.portq[i];
         for (int v = 0; v < DFD_NUM_VCS; v++) pq->pend_head[v] = pq->pend_tail[v] = pq->queue_head[v] = pq->queue_tail[v] = NIL;
     }
+    size_t nent = (size_t)P.NR * P.rheap_cap;
+    for (size_t i = gtid; i < nent; i += nthreads) {
+        unsigned k = (unsigned)(i % P.rheap_cap);
+        A.pent[i].next = (k + 1 < (unsigned)P.rheap_cap) ? k + 1 : NIL;
+    }
+    size_t nbk = (size_t)P.NR * P.wheel_nb;
+    for (size_t i = gtid; i < nbk; i += nthreads) A.wheel[i] = NIL;
+    for (size_t i = gtid; i < (nbk >> 6); i += nthreads) A.wbits[i] = 0ULL;
     size_t nslots = (size_t)P.NR * P.rpool_cap;
     for (size_t i = gtid; i < nslots; i += nthreads) {
         unsigned k = (unsigned)(i % P.rpool_cap);
@@ -1913,10 +1870,9 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.port, NR * P.radix)) return 1;
     if (dalloc(dev, &A.portq, NR * P.radix)) return 1;
     if (dalloc(dev, &A.pool, NR * P.rpool_cap)) return 1;
-    if (dalloc(dev, &A.rts, NR * P.rheap_cap)) return 1;
-    if (dalloc(dev, &A.rmeta, NR * P.rheap_cap)) return 1;
-    if (dalloc(dev, &A.nts, NR * P.rheap_cap)) return 1;
-    if (dalloc(dev, &A.nmeta, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.pent, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.wheel, NR * (size_t)P.wheel_nb)) return 1;
+    if (dalloc(dev, &A.wbits, NR * (size_t)(P.wheel_nb >> 6))) return 1;
     // exchange region: everything another rank may write (router inboxes and their tails, ACK statistics), behind
     // the sync block -- one allocation, one CUDA-IPC handle
     size_t off = align256(sizeof(DfdSync));

@@ -642,6 +642,7 @@ const char* device_error_name(unsigned long long code) {
     case DFD_ERR_LATE_EVENT: return "event scheduled inside the current window";
     case DFD_ERR_PEER_TIMEOUT: return "a peer GPU did not reach the window barrier";
     case DFD_ERR_PEER_ERROR: return "a peer GPU reported an error";
+    case DFD_ERR_WHEEL_RANGE: return "event delay outside the range of the router timing wheel";
     case DFD_ERR_REASM_OVERFLOW: return "too many messages being reassembled at one terminal (raise DFD_REASM_CAP)";
     }
     return "unknown";
@@ -939,7 +940,18 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->rcin_cap = (int)in_chunks;
     P->rkin_cap = (int)out_chunks;
     P->rpool_cap = (int)(in_chunks + out_chunks);
-    P->rheap_cap = (int)((in_chunks + out_chunks + p.radix + 1) & ~1LL);  // even: scanned two timestamps per load
+    P->rheap_cap = (int)(in_chunks + out_chunks + p.radix + 1);
+    {   // timing wheel: must span the largest delay between a router event's creation and its timestamp
+        double maxbw_inj = std::max(h_bytes_to_ns(p.chunk_size, p.cn_bandwidth), std::max(h_bytes_to_ns(p.chunk_size, p.local_bandwidth), h_bytes_to_ns(p.chunk_size, p.global_bandwidth)));
+        double maxdelay = std::max(p.cn_delay, std::max(p.local_delay, p.global_delay));
+        double maxcredit = std::max(p.cn_credit_delay, std::max(p.local_credit_delay, p.global_credit_delay));
+        double span = std::max(2.0 * maxbw_inj + p.router_delay + maxdelay, maxcredit) + 2.0 * L;
+        const double bucket = 4.0 * L;  // bucket width: a window overlaps at most two buckets; 4x fewer heads to keep warm
+        double nb = span / bucket + 8.0;
+        if (nb > 1048576.0) return fail(e, "the ratio of the largest link delay (%g ns) to the lookahead window (%g ns) is too large for the timing wheel; set an explicit credit_delay", span, L);
+        P->wheel_nb = std::max(64, next_pow2((int)nb + 1));
+        P->inv_window = 1.0 / bucket;
+    }
     return 0;
 }
 
@@ -1000,7 +1012,7 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
         reuse = Q.NT == P.NT && Q.NR == P.NR && Q.radix == P.radix && Q.a == P.a && Q.p == P.p && Q.G == P.G && Q.h == P.h &&
                 Q.ncin_cap == P.ncin_cap && Q.nkin_cap == P.nkin_cap && Q.nsq_cap == P.nsq_cap && Q.ntq_cap == P.ntq_cap &&
                 Q.nev_cap == P.nev_cap && Q.nreasm_cap == P.nreasm_cap && Q.rcin_cap == P.rcin_cap && Q.rkin_cap == P.rkin_cap &&
-                Q.rpool_cap == P.rpool_cap && Q.rheap_cap == P.rheap_cap;
+                Q.rpool_cap == P.rpool_cap && Q.rheap_cap == P.rheap_cap && Q.wheel_nb == P.wheel_nb;
     }
     if (reuse) {
         e->dev.P = P;

@@ -104,13 +104,15 @@ struct __attribute__((aligned(16))) PoolSlot {
     uint32_t origin_router, src_svr, dst_svr, dst_router;
 };
 
-// A router's pending events live in an unsorted structure-of-arrays list: timestamps in one array (scanned
-// with independent 16-byte loads to find the minimum), tie-break key + payload reference in another.
-struct __attribute__((aligned(16))) RPendMeta {
+// A router's pending events (chunk arrivals, credits, its own R_SEND timers) sit in a timing wheel: bucket
+// b = floor(ts / (4 * window)) mod wheel_nb holds a singly linked list of entries; a bitmap marks non-empty buckets.
+// Push is O(1); a window [T, T+L) only has to look at the (at most three) buckets it overlaps.
+struct __attribute__((aligned(8))) PendEnt {
+    double ts;
     uint32_t src;
     uint32_t seq;
-    uint32_t ref;  // kind<<28 | payload (pool slot / port | vc<<16)
-    uint32_t pad;
+    uint32_t ref;   // kind<<28 | payload (pool slot / port | vc<<16)
+    uint32_t next;  // next entry of the bucket, or of the free list
 };
 enum { RK_CHUNK = 1, RK_CREDIT = 2, RK_SEND = 3 };
 
@@ -137,14 +139,14 @@ struct __attribute__((aligned(16))) PortQ {
 struct __attribute__((aligned(16))) RouterHdr {
     int32_t rng[4];  // CLCG4 stream gid*3+0
     uint32_t seq;
-    uint32_t far_n;      // entries of the far pending list
+    uint32_t pend_n;     // pending events (entries in the wheel)
     uint32_t pool_free;  // head of the free list
     uint32_t gid;        // codes_mapping gid of this router
     uint16_t lid, grp;   // id inside the group, group id
-    uint32_t near_n;     // entries of the near pending list
+    uint32_t pent_free;  // head of the free list of wheel entries
     uint32_t pool_used;
     uint32_t heap_hwm;
-    double far_min;      // exact minimum timestamp of the far list (+inf when empty)
+    double pad_f;
     unsigned long long rng_draws;
 };
 
@@ -250,6 +252,8 @@ struct DfdParams {
     int ncin_cap, nkin_cap, nsq_cap, ntq_cap, nev_cap;
     int nreasm_cap;  // per-terminal reassembly table entries (0: every message is one chunk)
     int rcin_cap, rkin_cap, rpool_cap, rheap_cap;
+    int wheel_nb;        // buckets of a router's timing wheel (power of two, >= max event delay / window + slack)
+    double inv_window;   // 1 / (wheel bucket width)
 };
 
 // device arrays
@@ -277,10 +281,9 @@ struct DfdArrays {
     PortState* port;      // [NR][radix]
     PortQ* portq;         // [NR][radix]
     PoolSlot* pool;       // [NR][rpool_cap]
-    double* rts;          // [NR][rheap_cap]  far pending list: timestamps
-    RPendMeta* rmeta;     // [NR][rheap_cap]  far pending list: keys + payload references
-    double* nts;          // [NR][rheap_cap]  near pending list (due within a few windows)
-    RPendMeta* nmeta;     // [NR][rheap_cap]
+    PendEnt* pent;               // [NR][rheap_cap]   wheel entries
+    unsigned* wheel;             // [NR][wheel_nb]    bucket heads
+    unsigned long long* wbits;   // [NR][wheel_nb/64] non-empty-bucket bitmap
     ChunkRec* rcin;       // [NR][rcin_cap]
     CreditRec* rkin;      // [NR][rkin_cap]
     unsigned* rcin_tail;  // [NR]
@@ -319,4 +322,4 @@ struct DfdPeers {
 
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,
        DFD_ERR_HEAP_OVERFLOW, DFD_ERR_INBOX_OVERFLOW, DFD_ERR_DEAD_END, DFD_ERR_WRONG_TERMINAL, DFD_ERR_BAD_VC, DFD_ERR_SELF_SEND,
-       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR, DFD_ERR_REASM_OVERFLOW };
+       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR, DFD_ERR_REASM_OVERFLOW, DFD_ERR_WHEEL_RANGE };
