@@ -148,7 +148,7 @@ template <typename T> __device__ __forceinline__ T* on_rank(const DfdPeers& X, T
 // ------------------------------------------------------------------------------------------------
 // chunk towards a router: append to the router's inbox of the NEXT window parity (drained by the
 // router at the start of the next window, so a record is never read in the window it is written in)
-__device__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
+__device__ __forceinline__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const DfdPeers& X = *c.X;
@@ -174,7 +174,7 @@ __device__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
     for (int i = 0; i < 6; i++) __stcg(dst + i, src[i]);
     c.cand = fmin(c.cand, rec.ts);
 }
-__device__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc) {
+__device__ __forceinline__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const DfdPeers& X = *c.X;
@@ -210,7 +210,7 @@ __device__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned sr
 }
 // chunk / credit towards a terminal: single-producer rings (the only sender is the router the terminal
 // hangs off); an empty slot holds ts = +inf, the consumer restores that when it pops.
-__device__ void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
+__device__ __forceinline__ void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     if (rec.ts >= P.ts_end) return;
@@ -229,7 +229,7 @@ __device__ void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
     atomicMin(&A.wake_in[(size_t)c.nxt * P.NT + n], d2bits(rec.ts));
     c.cand = fmin(c.cand, rec.ts);
 }
-__device__ void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src, unsigned seq) {
+__device__ __forceinline__ void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src, unsigned seq) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     if (ts >= P.ts_end) return;
@@ -793,6 +793,8 @@ struct RCtx {
     PortState* port;
     PortQ* pq;
     PoolSlot* pool;
+    unsigned* pfree;            // stack of free pool-slot indices
+    unsigned* efree;            // stack of free wheel-entry indices
     PendEnt* pent;              // wheel entries
     unsigned* wheel;            // bucket heads
     unsigned long long* wbits;  // non-empty-bucket bitmap
@@ -805,14 +807,13 @@ __device__ __forceinline__ long long wheel_bucket(const DfdParams& P, double ts)
 __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
     const DfdParams& P = *c.P;
     if (ts >= P.ts_end) return;
-    unsigned e = R.h->pent_free;
     long long b = wheel_bucket(P, ts);
-    if (e == NIL || b - R.b_beg >= (long long)P.wheel_nb || b < R.b_beg) {
-        set_error(*c.A, e == NIL ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE, R.r);
+    if (R.h->ent_nfree == 0 || b - R.b_beg >= (long long)P.wheel_nb || b < R.b_beg) {
+        set_error(*c.A, R.h->ent_nfree == 0 ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE, R.r);
         return;
     }
+    unsigned e = R.efree[--R.h->ent_nfree];
     PendEnt* pe = &R.pent[e];
-    R.h->pent_free = pe->next;
     unsigned bi = (unsigned)b & (unsigned)(P.wheel_nb - 1);
     unsigned head = R.wheel[bi];
     pe->ts = ts;
@@ -828,7 +829,7 @@ __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned 
 
 // earliest pending event with ts < t_end, by (ts, src, seq), searched in the buckets the window overlaps; unlinks
 // it and returns its payload reference (or 0 when nothing is due)
-__device__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
+__device__ __forceinline__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
     const DfdParams& P = *c.P;
     const unsigned mask = (unsigned)(P.wheel_nb - 1);
     const long long b_end = wheel_bucket(P, c.t_end);
@@ -859,8 +860,7 @@ __device__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
         if (nxt == NIL) R.wbits[best_b >> 6] &= ~(1ULL << (best_b & 63));
     } else
         R.pent[best_prev].next = nxt;
-    pe->next = R.h->pent_free;
-    R.h->pent_free = best;
+    R.efree[R.h->ent_nfree++] = best;
     R.h->pend_n--;
     *now_out = bts;
     return ref;
@@ -868,7 +868,7 @@ __device__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
 
 // exact timestamp of the earliest pending event: the minimum of the first non-empty bucket at or after the window
 // start (bucket index is monotone in the timestamp, so no later bucket can hold an earlier event)
-__device__ double rwheel_next_ts(Ctx& c, RCtx& R) {
+__device__ __forceinline__ double rwheel_next_ts(Ctx& c, RCtx& R) {
     const DfdParams& P = *c.P;
     if (R.h->pend_n == 0) return DINF;
     const unsigned nb = (unsigned)P.wheel_nb, mask = nb - 1, nwords = nb >> 6;
@@ -913,7 +913,7 @@ __device__ __forceinline__ void grp_range(const DfdParams& P, const DfdArrays& A
 struct Cands {
     int kind, lo, hi, n;
 };
-__device__ int routed_count(const DfdParams& P, const DfdArrays& A, const RCtx& R, int g) {
+__device__ __forceinline__ int routed_count(const DfdParams& P, const DfdArrays& A, const RCtx& R, int g) {
     int o0 = A.routed_off[R.grp * P.G + g], o1 = A.routed_off[R.grp * P.G + g + 1];
     int n = 0;
     for (int i = o0; i < o1; i++) {
@@ -922,7 +922,7 @@ __device__ int routed_count(const DfdParams& P, const DfdArrays& A, const RCtx& 
     }
     return n;
 }
-__device__ int cand_port(const DfdParams& P, const DfdArrays& A, const RCtx& R, const Cands& cd, int idx) {
+__device__ __forceinline__ int cand_port(const DfdParams& P, const DfdArrays& A, const RCtx& R, const Cands& cd, int idx) {
     if (cd.kind == 1) return A.gs_port[(size_t)R.r * P.h + cd.lo + idx];
     if (cd.kind == 3) return A.loc_port[cd.lo + idx];
     // kind 2
@@ -936,7 +936,7 @@ __device__ int cand_port(const DfdParams& P, const DfdArrays& A, const RCtx& R, 
     return -1;
 }
 // get_legal_minimal_stops dally:9793-9849
-__device__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, const RCtx& R, int fdest_router, int fg) {
+__device__ __forceinline__ Cands legal_minimal_stops(const DfdParams& P, const DfdArrays& A, const RCtx& R, int fdest_router, int fg) {
     Cands cd;
     if (R.grp != fg) {
         grp_range(P, A, R.r, fg, &cd.lo, &cd.hi);
@@ -970,7 +970,7 @@ __device__ __forceinline__ int score_port(const DfdParams& P, const RCtx& R, int
 __device__ __forceinline__ long long r_integer(RCtx& R, long long lo, long long hi) { return clcg4_integer(R.h->rng, lo, hi, &R.h->rng_draws); }
 
 // get_absolute_best_connection_from_conns dally:1687-1723 over a candidate list
-__device__ int best_from_cands(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
+__device__ __forceinline__ int best_from_cands(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
     if (cd.n == 0) return -1;
     if (cd.n == 1) return cand_port(P, A, R, cd, 0);
     int best_score = 2147483647, nbest = 0;
@@ -993,7 +993,7 @@ __device__ int best_from_cands(const DfdParams& P, const DfdArrays& A, RCtx& R, 
     return -1;
 }
 // dfdally_get_best_from_k_connections dally:1796-1859 with k == 2
-__device__ int best_from_k2(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
+__device__ __forceinline__ int best_from_k2(const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd) {
     if (cd.n == 0) return -1;
     if (cd.n == 1) return cand_port(P, A, R, cd, 0);
     long long n = cd.n;
@@ -1015,7 +1015,7 @@ __device__ int best_from_k2(const DfdParams& P, const DfdArrays& A, RCtx& R, con
 }
 
 // dfdally_select_intermediate_group dally:9738-9790
-__device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
+__device__ __forceinline__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
     int fg = m.dst_grp;
     int og = m.org_grp;
     if (m.intm_grp_id == -1) {
@@ -1051,7 +1051,7 @@ __device__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A
 }
 
 // get_legal_nonminimal_stops dally:9853-9910
-__device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
+__device__ __forceinline__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
     Cands cd;
     cd.kind = 0;
     cd.lo = cd.hi = cd.n = 0;
@@ -1079,7 +1079,7 @@ __device__ Cands legal_nonminimal_stops(const DfdParams& P, const DfdArrays& A, 
 }
 
 // do_dfdally_routing dally:7110-7215 -> output port
-__device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
+__device__ __forceinline__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     int fg = m.dst_grp;
@@ -1148,8 +1148,28 @@ __device__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdest_router) {
     return best_non;
 }
 
+// 4-element arrays held in registers: select / update by index without dynamic addressing (which would push the
+// whole struct to local memory)
+template <typename T> __device__ __forceinline__ T get4(const T* a, int i) { return i == 0 ? a[0] : i == 1 ? a[1] : i == 2 ? a[2] : a[3]; }
+template <typename T> __device__ __forceinline__ void set4(T* a, int i, T v) {
+    if (i == 0) a[0] = v;
+    else if (i == 1) a[1] = v;
+    else if (i == 2) a[2] = v;
+    else a[3] = v;
+}
+// whole-struct copies as 128-bit accesses (all of these structs are 16-byte aligned multiples of 16 bytes)
+template <typename T> __device__ __forceinline__ void load_vec(T& dst, const T* src) {
+    static_assert(sizeof(T) % 16 == 0, "vector copy");
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) ((int4*)&dst)[i] = ((const int4*)src)[i];
+}
+template <typename T> __device__ __forceinline__ void store_vec(T* dst, const T& src) {
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) ((int4*)dst)[i] = ((const int4*)&src)[i];
+}
+
 // router_credit_send dally:7269-7326
-__device__ void router_credit_send(Ctx& c, RCtx& R, double now, unsigned last_hop, unsigned prev_lp, unsigned port, unsigned vc) {
+__device__ __forceinline__ void router_credit_send(Ctx& c, RCtx& R, double now, unsigned last_hop, unsigned prev_lp, unsigned port, unsigned vc) {
     const DfdParams& P = *c.P;
     unsigned seq = R.h->seq++;
     if (last_hop == DFD_HOP_TERMINAL)
@@ -1176,10 +1196,11 @@ __device__ __forceinline__ unsigned fifo_pop(PoolSlot* pool, uint32_t* head, uin
 }
 
 // router_packet_receive dally:7377-7595; the chunk already sits in pool slot `slot`
-__device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot) {
+__device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
-    PoolSlot& m = R.pool[slot];
+    PoolSlot m;  // the chunk: read once, routed in registers, written back once
+    load_vec(m, &R.pool[slot]);
     int dest_router_id = (int)m.dst_router;
     int in_path_type = m.path_type;  // msg->path_type (as received)
     unsigned in_port = m.prev_port, in_vc = m.prev_vc, in_last_hop = m.last_hop, in_prev = m.prev_lp;
@@ -1189,6 +1210,10 @@ __device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot
         set_error(A, DFD_ERR_DEAD_END, R.r);
         return;
     }
+    PortState ps;
+    PortQ pq;
+    load_vec(ps, &R.port[output_port]);
+    load_vec(pq, &R.pq[output_port]);
     int conn_local = output_port < P.intra_radix;
     int conn_global = !conn_local && output_port < P.intra_radix + P.global_radix;
     if (conn_local) {
@@ -1231,12 +1256,17 @@ __device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot
     }
     m.out_vc = (uint8_t)output_chan;
     m.n_hop++;
-    PortState& ps = R.port[output_port];
-    PortQ& pq = R.pq[output_port];
-    if (ps.vc_occ[output_chan] + P.chunk_size <= max_vc_size) {
+    m.next = NIL;
+    int occ = get4(ps.vc_occ, output_chan);
+    if (occ + P.chunk_size <= max_vc_size) {
         router_credit_send(c, R, now, in_last_hop, in_prev, in_port, in_vc);
-        fifo_append(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan], slot);
-        ps.vc_occ[output_chan] += P.chunk_size;
+        unsigned tl = get4(pq.pend_tail, output_chan);  // append to pending_msgs[port][vc]
+        if (tl == NIL)
+            set4(pq.pend_head, output_chan, slot);
+        else
+            R.pool[tl].next = slot;
+        set4(pq.pend_tail, output_chan, slot);
+        set4(ps.vc_occ, output_chan, occ + P.chunk_size);
         if (ps.in_send_loop == 0) {
             double ts = maxd(ps.noat, now) - now;
             rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
@@ -1245,36 +1275,50 @@ __device__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot
     } else {
         ps.stalled_chunks++;
         // saved_vc / saved_channel = upstream port / vc: already kept in prev_port / prev_vc
-        fifo_append(R.pool, &pq.queue_head[output_chan], &pq.queue_tail[output_chan], slot);
+        unsigned tl = get4(pq.queue_tail, output_chan);  // append to queued_msgs[port][vc]
+        if (tl == NIL)
+            set4(pq.queue_head, output_chan, slot);
+        else
+            R.pool[tl].next = slot;
+        set4(pq.queue_tail, output_chan, slot);
         ps.queued_count += P.chunk_size;
         if (ps.last_buf_full == 0.0) ps.last_buf_full = now;
     }
+    store_vec(&R.pool[slot], m);
+    store_vec(&R.port[output_port], ps);
+    store_vec(&R.pq[output_port], pq);
 }
 
 // router_packet_send dally:7705-8032 (+ get_next_router_vcg :3499-3557)
-__device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port) {
+__device__ __forceinline__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port) {
     const DfdParams& P = *c.P;
-    PortState& ps = R.port[output_port];
-    PortQ& pq = R.pq[output_port];
+    PortState ps;
+    PortQ pq;
+    load_vec(ps, &R.port[output_port]);
+    load_vec(pq, &R.pq[output_port]);
     int output_chan = -1;
     {
         int next_rr_vc = (ps.last_qos_lvl + 1) % DFD_NUM_VCS;
+#pragma unroll
         for (int i = 0; i < DFD_NUM_VCS; i++) {
-            if (pq.pend_head[next_rr_vc] != NIL) {
-                ps.last_qos_lvl = (uint8_t)next_rr_vc;
-                output_chan = next_rr_vc;
-                break;
+            if (output_chan < 0) {
+                if (get4(pq.pend_head, next_rr_vc) != NIL) {
+                    ps.last_qos_lvl = (uint8_t)next_rr_vc;
+                    output_chan = next_rr_vc;
+                } else
+                    next_rr_vc = (next_rr_vc + 1) % DFD_NUM_VCS;
             }
-            next_rr_vc = (next_rr_vc + 1) % DFD_NUM_VCS;
         }
     }
     if (output_chan < 0) {
         ps.in_send_loop = 0;
         if (ps.queued_count && !ps.last_buf_full) ps.last_buf_full = now;
+        store_vec(&R.port[output_port], ps);
         return;
     }
-    unsigned slot = pq.pend_head[output_chan];
-    PoolSlot& m = R.pool[slot];
+    unsigned slot = get4(pq.pend_head, output_chan);
+    PoolSlot m;
+    load_vec(m, &R.pool[slot]);
     if (ps.last_buf_full) {
         ps.busy_time += (now - ps.last_buf_full);
         ps.last_buf_full = 0.0;
@@ -1304,14 +1348,12 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
     double propagation_ts = injection_ts + propagation_delay;
     {
         // outgoing record = the pool slot with a new key and the "previous hop" fields replaced; the two
-        // layouts agree from byte 16 on, so this is a vector copy plus two patched words
+        // layouts agree from byte 16 on
         union {
             ChunkRec rec;
-            int4 v[6];
+            PoolSlot slot;
         } u;
-        const int4* sv = (const int4*)&m;
-#pragma unroll
-        for (int i = 1; i < 6; i++) u.v[i] = sv[i];
+        u.slot = m;
         u.rec.ts = now + propagation_ts;
         u.rec.src = R.gid;
         u.rec.seq = R.h->seq++;
@@ -1329,48 +1371,63 @@ __device__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port)
     else
         ps.link_traffic += P.chunk_size;
     ps.total_chunks++;
-    fifo_pop(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan]);
-    R.pool[slot].next = R.h->pool_free;  // free the slot
-    R.h->pool_free = slot;
-    R.h->pool_used--;
+    set4(pq.pend_head, output_chan, m.next);  // pop pending_msgs[port][vc]
+    if (m.next == NIL) set4(pq.pend_tail, output_chan, NIL);
+    R.pfree[R.h->pool_nfree++] = slot;  // free the slot
     ps.noat -= P.router_delay;
     injection_ts -= P.router_delay;
-    int next_output_chan = -1;
-    for (int k = 0; k < DFD_NUM_VCS; k++)
-        if (pq.pend_head[k] != NIL) {
-            next_output_chan = k;
-            break;
-        }
-    if (next_output_chan < 0) {
+    bool more = (pq.pend_head[0] != NIL) | (pq.pend_head[1] != NIL) | (pq.pend_head[2] != NIL) | (pq.pend_head[3] != NIL);
+    if (!more)
         ps.in_send_loop = 0;
-        return;
-    }
-    rheap_push(c, R, now + injection_ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
+    else
+        rheap_push(c, R, now + injection_ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
+    store_vec(&R.port[output_port], ps);
+    store_vec(&R.pq[output_port], pq);
 }
 
 // router_buf_update dally:8069-8145
-__device__ void router_buf_update(Ctx& c, RCtx& R, double now, int indx, int output_chan) {
+__device__ __forceinline__ void router_buf_update(Ctx& c, RCtx& R, double now, int indx, int output_chan) {
     const DfdParams& P = *c.P;
-    PortState& ps = R.port[indx];
-    PortQ& pq = R.pq[indx];
-    ps.vc_occ[output_chan] -= P.chunk_size;
+    PortState ps;
+    PortQ pq;
+    load_vec(ps, &R.port[indx]);
+    load_vec(pq, &R.pq[indx]);
+    int occ = get4(ps.vc_occ, output_chan) - P.chunk_size;
     if (ps.last_buf_full > 0.0) {
         ps.busy_time += (now - ps.last_buf_full);
         ps.last_buf_full = 0.0;
     }
-    if (pq.queue_head[output_chan] != NIL) {
-        unsigned slot = fifo_pop(R.pool, &pq.queue_head[output_chan], &pq.queue_tail[output_chan]);
-        PoolSlot& hd = R.pool[slot];
-        router_credit_send(c, R, now, hd.last_hop, hd.prev_lp, hd.prev_port, hd.prev_vc);
-        fifo_append(R.pool, &pq.pend_head[output_chan], &pq.pend_tail[output_chan], slot);
-        ps.vc_occ[output_chan] += P.chunk_size;
+    unsigned qh = get4(pq.queue_head, output_chan);
+    if (qh != NIL) {  // promote the oldest overflowed chunk: credit its sender, move it to pending_msgs
+        const PoolSlot* hd = &R.pool[qh];
+        int4 v0 = ((const int4*)hd)[0];
+        int4 v3 = ((const int4*)hd)[3];
+        unsigned nxt = (unsigned)v0.x;                        // next
+        unsigned prev_lp = (unsigned)v3.x;                    // prev_lp
+        unsigned prev_port = (unsigned)v3.y & 0xFFFFu;        // prev_port
+        unsigned prev_vc = ((unsigned)v3.y >> 16) & 0xFFu;    // prev_vc
+        unsigned last_hop = ((unsigned)v3.y >> 24) & 0xFFu;   // last_hop
+        set4(pq.queue_head, output_chan, nxt);
+        if (nxt == NIL) set4(pq.queue_tail, output_chan, NIL);
+        router_credit_send(c, R, now, last_hop, prev_lp, prev_port, prev_vc);
+        R.pool[qh].next = NIL;
+        unsigned tl = get4(pq.pend_tail, output_chan);
+        if (tl == NIL)
+            set4(pq.pend_head, output_chan, qh);
+        else
+            R.pool[tl].next = qh;
+        set4(pq.pend_tail, output_chan, qh);
+        occ += P.chunk_size;
         ps.queued_count -= P.chunk_size;
     }
-    if (ps.in_send_loop == 0 && pq.pend_head[output_chan] != NIL) {
+    set4(ps.vc_occ, output_chan, occ);
+    if (ps.in_send_loop == 0 && get4(pq.pend_head, output_chan) != NIL) {
         double ts = maxd(ps.noat, now) - now;
         rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)indx);
         ps.in_send_loop = 1;
     }
+    store_vec(&R.port[indx], ps);
+    store_vec(&R.pq[indx], pq);
 }
 
 __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned ntail_k) {
@@ -1381,7 +1438,8 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
 #endif
     RCtx R;
     R.r = r;
-    R.h = &A.rh[r];
+    RouterHdr hd = A.rh[r];  // header lives in registers for the whole activation, written back once at the end
+    R.h = &hd;
     R.gid = R.h->gid;
     R.lid = R.h->lid;
     R.grp = R.h->grp;
@@ -1389,6 +1447,8 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     R.pq = &A.portq[(size_t)r * P.radix];
     R.pool = &A.pool[(size_t)r * P.rpool_cap];
     R.pent = &A.pent[(size_t)r * P.rheap_cap];
+    R.pfree = &A.pfree[(size_t)r * P.rpool_cap];
+    R.efree = &A.efree[(size_t)r * P.rheap_cap];
     R.wheel = &A.wheel[(size_t)r * P.wheel_nb];
     R.wbits = &A.wbits[(size_t)r * (P.wheel_nb >> 6)];
     R.b_beg = c.b_beg;
@@ -1399,13 +1459,11 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     if (ntail_c) {
         const ChunkRec* in = &A.rcin[((size_t)c.cur * P.NR + r) * P.rcin_cap];
         for (unsigned i = 0; i < ntail_c; i++) {
-            unsigned slot = R.h->pool_free;
-            if (slot == NIL) {
+            if (R.h->pool_nfree == 0) {
                 set_error(A, DFD_ERR_POOL_OVERFLOW, r);
                 break;
             }
-            R.h->pool_free = R.pool[slot].next;
-            R.h->pool_used++;
+            unsigned slot = R.pfree[--R.h->pool_nfree];
             int4 v0 = __ldcg((const int4*)&in[i]);
             int4* dst = (int4*)&R.pool[slot];
 #pragma unroll
@@ -1460,6 +1518,7 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
         }
     }
     double next_ts = rwheel_next_ts(c, R);
+    A.rh[r] = hd;
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
 #ifdef DFD_PROFILE
@@ -1759,8 +1818,8 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         RouterHdr* h = &A.rh[r];
         memset(h, 0, sizeof(RouterHdr));
         seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
-        h->pool_free = 0;
-        h->pent_free = 0;
+        h->pool_nfree = (uint32_t)P.rpool_cap;
+        h->ent_nfree = (uint32_t)P.rheap_cap;
         h->gid = rtr_gid(P, r);
         h->lid = (uint16_t)(r % P.a);
         h->grp = (uint16_t)(r / P.a);
@@ -1781,7 +1840,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
     size_t nent = (size_t)P.NR * P.rheap_cap;
     for (size_t i = gtid; i < nent; i += nthreads) {
         unsigned k = (unsigned)(i % P.rheap_cap);
-        A.pent[i].next = (k + 1 < (unsigned)P.rheap_cap) ? k + 1 : NIL;
+        A.efree[i] = (unsigned)P.rheap_cap - 1 - k;  // popped from the top: entry 0 first
     }
     size_t nbk = (size_t)P.NR * P.wheel_nb;
     for (size_t i = gtid; i < nbk; i += nthreads) A.wheel[i] = NIL;
@@ -1789,7 +1848,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
     size_t nslots = (size_t)P.NR * P.rpool_cap;
     for (size_t i = gtid; i < nslots; i += nthreads) {
         unsigned k = (unsigned)(i % P.rpool_cap);
-        A.pool[i].next = (k + 1 < (unsigned)P.rpool_cap) ? k + 1 : NIL;
+        A.pfree[i] = (unsigned)P.rpool_cap - 1 - k;
     }
 }
 
@@ -1871,6 +1930,8 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.portq, NR * P.radix)) return 1;
     if (dalloc(dev, &A.pool, NR * P.rpool_cap)) return 1;
     if (dalloc(dev, &A.pent, NR * P.rheap_cap)) return 1;
+    if (dalloc(dev, &A.pfree, NR * P.rpool_cap)) return 1;
+    if (dalloc(dev, &A.efree, NR * P.rheap_cap)) return 1;
     if (dalloc(dev, &A.wheel, NR * (size_t)P.wheel_nb)) return 1;
     if (dalloc(dev, &A.wbits, NR * (size_t)(P.wheel_nb >> 6))) return 1;
     // exchange region: everything another rank may write (router inboxes and their tails, ACK statistics), behind

@@ -140,10 +140,10 @@ struct __attribute__((aligned(16))) RouterHdr {
     int32_t rng[4];  // CLCG4 stream gid*3+0
     uint32_t seq;
     uint32_t pend_n;     // pending events (entries in the wheel)
-    uint32_t pool_free;  // head of the free list
+    uint32_t pool_nfree; // entries on the free-slot stack
     uint32_t gid;        // codes_mapping gid of this router
     uint16_t lid, grp;   // id inside the group, group id
-    uint32_t pent_free;  // head of the free list of wheel entries
+    uint32_t ent_nfree;  // entries on the free wheel-entry stack
     uint32_t pool_used;
     uint32_t heap_hwm;
     double pad_f;
@@ -282,6 +282,8 @@ struct DfdArrays {
     PortQ* portq;         // [NR][radix]
     PoolSlot* pool;       // [NR][rpool_cap]
     PendEnt* pent;               // [NR][rheap_cap]   wheel entries
+    unsigned* pfree;             // [NR][rpool_cap]   stack of free pool slots
+    unsigned* efree;             // [NR][rheap_cap]   stack of free wheel entries
     unsigned* wheel;             // [NR][wheel_nb]    bucket heads
     unsigned long long* wbits;   // [NR][wheel_nb/64] non-empty-bucket bitmap
     ChunkRec* rcin;       // [NR][rcin_cap]
