@@ -146,24 +146,15 @@ template <typename T> __device__ __forceinline__ T* on_rank(const DfdPeers& X, T
 // ------------------------------------------------------------------------------------------------
 // event delivery
 // ------------------------------------------------------------------------------------------------
-// chunk towards a router: append to the router's inbox of the NEXT window parity (drained by the
+// chunk towards a router on this GPU: append to the router's inbox of the NEXT window parity (drained by the
 // router at the start of the next window, so a record is never read in the window it is written in)
 __device__ __forceinline__ void push_chunk_to_router(Ctx& c, unsigned r, const ChunkRec& rec) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
-    const DfdPeers& X = *c.X;
     if (rec.ts >= P.ts_end) return;
     unsigned* tail = &A.rcin_tail[(size_t)c.nxt * P.NR + r];
     ChunkRec* box = &A.rcin[((size_t)c.nxt * P.NR + r) * P.rcin_cap];
-    unsigned idx;
-    int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(r, P.magic_a)) : X.rank;
-    if (owner != X.rank) {  // the router lives on another GPU: reserve and write through the NVLink mapping
-        tail = on_rank(X, tail, owner);
-        box = on_rank(X, box, owner);
-        idx = atomicAdd_system(tail, 1u);
-        c.remote_writes = true;
-    } else
-        idx = atomicAdd(tail, 1u);
+    unsigned idx = atomicAdd(tail, 1u);
     if (idx >= (unsigned)P.rcin_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
@@ -177,19 +168,10 @@ __device__ __forceinline__ void push_chunk_to_router(Ctx& c, unsigned r, const C
 __device__ __forceinline__ void push_credit_to_router(Ctx& c, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
-    const DfdPeers& X = *c.X;
     if (ts >= P.ts_end) return;
     unsigned* tail = &A.rkin_tail[(size_t)c.nxt * P.NR + r];
     CreditRec* box = &A.rkin[((size_t)c.nxt * P.NR + r) * P.rkin_cap];
-    unsigned idx;
-    int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(r, P.magic_a)) : X.rank;
-    if (owner != X.rank) {
-        tail = on_rank(X, tail, owner);
-        box = on_rank(X, box, owner);
-        idx = atomicAdd_system(tail, 1u);
-        c.remote_writes = true;
-    } else
-        idx = atomicAdd(tail, 1u);
+    unsigned idx = atomicAdd(tail, 1u);
     if (idx >= (unsigned)P.rkin_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
@@ -206,6 +188,80 @@ __device__ __forceinline__ void push_credit_to_router(Ctx& c, unsigned r, double
     int4* dst = (int4*)&box[idx];
     __stcg(dst, ((const int4*)&rec)[0]);
     __stcg(dst + 1, ((const int4*)&rec)[1]);
+    c.cand = fmin(c.cand, ts);
+}
+// Global link whose far end lives on another GPU.  Every such link direction has exactly one sending router, so
+// the receiver keeps one lane per (router, global port): the sender counts its own pushes, writes record, count
+// and lane bit as posted stores / reductions -- nothing has to return over NVLink inside a handler.
+__device__ __forceinline__ unsigned xlane_reserve(Ctx& c, unsigned my_port_idx, bool credit, unsigned* packed) {
+    uint2* sp = &c.A->xsend[my_port_idx];
+    uint2 v = *sp;
+    if (v.x != c.widx + 1u) {
+        v.x = c.widx + 1u;
+        v.y = 0;
+    }
+    unsigned idx = credit ? (v.y >> 16) : (v.y & 0xFFFFu);
+    v.y += credit ? 0x10000u : 1u;
+    *sp = v;
+    *packed = v.y;
+    return idx;
+}
+__device__ __forceinline__ void xlane_publish(Ctx& c, size_t lane, unsigned r, unsigned kp, unsigned packed, int owner) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    const DfdPeers& X = *c.X;
+    __stcg(on_rank(X, &A.xcnt[lane], owner), packed);
+    unsigned long long* mk = on_rank(X, &A.xmask[(size_t)c.nxt * P.NR + r], owner);
+    asm volatile("red.relaxed.sys.global.or.b64 [%0], %1;" ::"l"(mk), "l"(1ULL << kp) : "memory");
+    c.remote_writes = true;
+}
+__device__ __forceinline__ void push_chunk_remote(Ctx& c, unsigned me, unsigned my_gport, unsigned r, const ChunkRec& rec, int owner) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    const DfdPeers& X = *c.X;
+    if (rec.ts >= P.ts_end) return;
+    unsigned kp = (unsigned)A.grev[(size_t)me * P.h + my_gport];
+    size_t lane = ((size_t)c.nxt * P.NR + r) * P.h + kp;
+    unsigned packed;
+    unsigned idx = xlane_reserve(c, me * P.h + my_gport, false, &packed);
+    if (idx >= DFD_XLANE_CAP) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
+        return;
+    }
+    int4* dst = (int4*)on_rank(X, &A.xc[lane * DFD_XLANE_CAP + idx], owner);
+    const int4* src = (const int4*)&rec;
+#pragma unroll
+    for (int i = 0; i < 6; i++) __stcg(dst + i, src[i]);
+    xlane_publish(c, lane, r, kp, packed, owner);
+    c.cand = fmin(c.cand, rec.ts);
+}
+__device__ __forceinline__ void push_credit_remote(Ctx& c, unsigned me, unsigned r, double ts, unsigned src, unsigned seq, unsigned port, unsigned vc, int owner) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    const DfdPeers& X = *c.X;
+    if (ts >= P.ts_end) return;
+    unsigned kp = port - (unsigned)P.intra_radix;                   // the receiver's own port: its lane
+    unsigned my_gport = (unsigned)A.grev[(size_t)r * P.h + kp];     // my end of that link
+    size_t lane = ((size_t)c.nxt * P.NR + r) * P.h + kp;
+    unsigned packed;
+    unsigned idx = xlane_reserve(c, me * P.h + my_gport, true, &packed);
+    if (idx >= DFD_XLANE_CAP) {
+        set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
+        return;
+    }
+    CreditRec rec;
+    rec.ts = ts;
+    rec.src = src;
+    rec.seq = seq;
+    rec.port = (uint16_t)port;
+    rec.vc = (uint8_t)vc;
+    rec.pad0 = 0;
+    rec.pad1 = 0;
+    rec.pad2 = 0;
+    int4* dst = (int4*)on_rank(X, &A.xk[lane * DFD_XLANE_CAP + idx], owner);
+    __stcg(dst, ((const int4*)&rec)[0]);
+    __stcg(dst + 1, ((const int4*)&rec)[1]);
+    xlane_publish(c, lane, r, kp, packed, owner);
     c.cand = fmin(c.cand, ts);
 }
 // chunk / credit towards a terminal: single-producer rings (the only sender is the router the terminal
@@ -1174,25 +1230,15 @@ __device__ __forceinline__ void router_credit_send(Ctx& c, RCtx& R, double now, 
     unsigned seq = R.h->seq++;
     if (last_hop == DFD_HOP_TERMINAL)
         push_credit_to_node(c, prev_lp, now + P.cn_credit, R.gid, seq);
-    else if (last_hop == DFD_HOP_GLOBAL)
-        push_credit_to_router(c, prev_lp, now + P.global_credit, R.gid, seq, port, vc);
-    else
+    else if (last_hop == DFD_HOP_GLOBAL) {
+        const DfdPeers& X = *c.X;
+        int owner = X.world > 1 ? owner_of_group(X, (int)fastdiv(prev_lp, P.magic_a)) : X.rank;
+        if (owner != X.rank)
+            push_credit_remote(c, R.r, prev_lp, now + P.global_credit, R.gid, seq, port, vc, owner);
+        else
+            push_credit_to_router(c, prev_lp, now + P.global_credit, R.gid, seq, port, vc);
+    } else
         push_credit_to_router(c, prev_lp, now + P.local_credit, R.gid, seq, port, vc);
-}
-
-__device__ __forceinline__ void fifo_append(PoolSlot* pool, uint32_t* head, uint32_t* tail, unsigned slot) {
-    pool[slot].next = NIL;
-    if (*tail == NIL)
-        *head = slot;
-    else
-        pool[*tail].next = slot;
-    *tail = slot;
-}
-__device__ __forceinline__ unsigned fifo_pop(PoolSlot* pool, uint32_t* head, uint32_t* tail) {
-    unsigned s = *head;
-    *head = pool[s].next;
-    if (*head == NIL) *tail = NIL;
-    return s;
 }
 
 // router_packet_receive dally:7377-7595; the chunk already sits in pool slot `slot`
@@ -1363,8 +1409,14 @@ __device__ __forceinline__ void router_packet_send(Ctx& c, RCtx& R, double now, 
         u.rec.last_hop = global ? DFD_HOP_GLOBAL : DFD_HOP_LOCAL;
         if (to_terminal)
             push_chunk_to_node(c, m.next_stop, u.rec);
-        else
-            push_chunk_to_router(c, m.next_stop, u.rec);
+        else {
+            const DfdPeers& X = *c.X;
+            int owner = (global && X.world > 1) ? owner_of_group(X, (int)fastdiv(m.next_stop, P.magic_a)) : X.rank;
+            if (owner != X.rank)
+                push_chunk_remote(c, R.r, (unsigned)(output_port - P.intra_radix), m.next_stop, u.rec, owner);
+            else
+                push_chunk_to_router(c, m.next_stop, u.rec);
+        }
     }
     if ((tail || m.packet_size == 0) && (m.chunk_id == nchunks - 1))
         ps.link_traffic += tail;
@@ -1430,6 +1482,32 @@ __device__ __forceinline__ void router_buf_update(Ctx& c, RCtx& R, double now, i
     store_vec(&R.pq[indx], pq);
 }
 
+// inbox records -> pool slots / wheel entries
+__device__ __forceinline__ void drain_chunks(Ctx& c, RCtx& R, const ChunkRec* in, unsigned n) {
+    for (unsigned i = 0; i < n; i++) {
+        if (R.h->pool_nfree == 0) {
+            set_error(*c.A, DFD_ERR_POOL_OVERFLOW, R.r);
+            break;
+        }
+        unsigned slot = R.pfree[--R.h->pool_nfree];
+        int4 v0 = __ldcg((const int4*)&in[i]);
+        int4* dst = (int4*)&R.pool[slot];
+#pragma unroll
+        for (int k = 1; k < 6; k++) dst[k] = __ldcg((const int4*)&in[i] + k);
+        double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
+        rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CHUNK << 28) | slot);
+    }
+}
+__device__ __forceinline__ void drain_credits(Ctx& c, RCtx& R, const CreditRec* in, unsigned n) {
+    for (unsigned i = 0; i < n; i++) {
+        int4 v0 = __ldcg((const int4*)&in[i]);
+        int4 v1 = __ldcg((const int4*)&in[i] + 1);
+        double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
+        unsigned port = (unsigned)v1.x & 0xFFFFu, vc = ((unsigned)v1.x >> 16) & 0xFFu;
+        rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CREDIT << 28) | (vc << 16) | port);
+    }
+}
+
 __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned ntail_k) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
@@ -1457,32 +1535,27 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     long long pd0 = clock64();
 #endif
     if (ntail_c) {
-        const ChunkRec* in = &A.rcin[((size_t)c.cur * P.NR + r) * P.rcin_cap];
-        for (unsigned i = 0; i < ntail_c; i++) {
-            if (R.h->pool_nfree == 0) {
-                set_error(A, DFD_ERR_POOL_OVERFLOW, r);
-                break;
-            }
-            unsigned slot = R.pfree[--R.h->pool_nfree];
-            int4 v0 = __ldcg((const int4*)&in[i]);
-            int4* dst = (int4*)&R.pool[slot];
-#pragma unroll
-            for (int k = 1; k < 6; k++) dst[k] = __ldcg((const int4*)&in[i] + k);
-            double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
-            rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CHUNK << 28) | slot);
-        }
+        drain_chunks(c, R, &A.rcin[((size_t)c.cur * P.NR + r) * P.rcin_cap], ntail_c);
         A.rcin_tail[(size_t)c.cur * P.NR + r] = 0;
     }
     if (ntail_k) {
-        const CreditRec* in = &A.rkin[((size_t)c.cur * P.NR + r) * P.rkin_cap];
-        for (unsigned i = 0; i < ntail_k; i++) {
-            int4 v0 = __ldcg((const int4*)&in[i]);
-            int4 v1 = __ldcg((const int4*)&in[i] + 1);
-            double ts = __longlong_as_double(((long long)(unsigned)v0.y << 32) | (unsigned)v0.x);
-            unsigned port = (unsigned)v1.x & 0xFFFFu, vc = ((unsigned)v1.x >> 16) & 0xFFu;
-            rheap_push(c, R, ts, (unsigned)v0.z, (unsigned)v0.w, (RK_CREDIT << 28) | (vc << 16) | port);
-        }
+        drain_credits(c, R, &A.rkin[((size_t)c.cur * P.NR + r) * P.rkin_cap], ntail_k);
         A.rkin_tail[(size_t)c.cur * P.NR + r] = 0;
+    }
+    if (c.X->world > 1) {  // lanes of the global links that come from other GPUs
+        unsigned long long xm = __ldcg(&A.xmask[(size_t)c.cur * P.NR + r]);
+        if (xm) {
+            A.xmask[(size_t)c.cur * P.NR + r] = 0;
+            do {
+                unsigned kp = (unsigned)__ffsll((long long)xm) - 1u;
+                xm &= xm - 1;
+                size_t lane = ((size_t)c.cur * P.NR + r) * P.h + kp;
+                unsigned cnt = __ldcg(&A.xcnt[lane]);
+                A.xcnt[lane] = 0;
+                if (cnt & 0xFFFFu) drain_chunks(c, R, &A.xc[lane * DFD_XLANE_CAP], cnt & 0xFFFFu);
+                if (cnt >> 16) drain_credits(c, R, &A.xk[lane * DFD_XLANE_CAP], cnt >> 16);
+            } while (xm);
+        }
     }
 #ifdef DFD_PROFILE
     if (ntail_c | ntail_k) {
@@ -1561,41 +1634,57 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned l
 __device__ void peer_window_close(const DfdArrays& A, const DfdPeers& X, unsigned long long w) {
     const unsigned slot = (unsigned)((w + 1) % 3);
     unsigned long long m = __ldcg(&A.gmin[slot]);
-    unsigned long long myerr = __ldcg(&A.counters[2]);
+    const unsigned long long myerr = __ldcg(&A.counters[2]);
     DfdSync* mine = (DfdSync*)X.local_base;
-    __threadfence_system();
+    // one 8-byte store per peer is both the message and the flag: a slot holds DFD_SYNC_EMPTY until the peer's
+    // minimum (or DFD_SYNC_FAILED) lands in it.  Every block fenced its own remote records before it arrived at
+    // the local barrier, so nothing else has to be ordered here.
+    const unsigned long long msg = myerr ? DFD_SYNC_FAILED : m;
     for (int k = 0; k < X.world; k++) {
         if (k == X.rank) continue;
         DfdSync* peer = (DfdSync*)X.base[k];
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&peer->mins[slot][X.rank]), "l"(m) : "memory");
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&peer->err[X.rank]), "l"(myerr) : "memory");
-    }
-    __threadfence_system();
-    for (int k = 0; k < X.world; k++) {
-        if (k == X.rank) continue;
-        DfdSync* peer = (DfdSync*)X.base[k];
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&peer->flag[X.rank]), "l"(w + 1) : "memory");
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&peer->mins[slot][X.rank]), "l"(msg) : "memory");
     }
     unsigned long long err = myerr;
     for (int k = 0; k < X.world; k++) {
         if (k == X.rank) continue;
-        unsigned long long f;
+        unsigned long long pm;
         unsigned long long spins = 0;
         do {
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&mine->flag[k]) : "memory");
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pm) : "l"(&mine->mins[slot][k]) : "memory");
             if (++spins > (1ULL << 27)) {  // ~ a minute of polling
                 err = DFD_ERR_PEER_TIMEOUT;
                 break;
             }
-        } while (f < w + 1);
-        unsigned long long pm, pe;
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pm) : "l"(&mine->mins[slot][k]) : "memory");
-        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(pe) : "l"(&mine->err[k]) : "memory");
-        if (pm < m) m = pm;
-        if (pe && !err) err = DFD_ERR_PEER_ERROR;
+        } while (pm == DFD_SYNC_EMPTY);
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(&mine->mins[slot][k]), "l"(DFD_SYNC_EMPTY) : "memory");  // re-arm for window w + 3
+        if (pm == DFD_SYNC_FAILED) {
+            if (!err) err = DFD_ERR_PEER_ERROR;
+        } else if (pm < m)
+            m = pm;
     }
     __stcg(&A.gmin[slot], m);
     if (err && !myerr) set_error(A, (unsigned)err, 0);
+}
+// Window close of a sharded run: one local barrier whose last arriving block exchanges minima and completion
+// flags with the other GPUs before it releases the rest through the go word.
+__device__ __forceinline__ void grid_barrier_peers(const DfdArrays& A, const DfdPeers& X, unsigned long long w, unsigned long long* ctr,
+                                                   unsigned long long target, unsigned long long* go) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long old;
+        asm volatile("atom.release.gpu.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(ctr), "l"(1ULL) : "memory");
+        if (old + 1 == target) {
+            peer_window_close(A, X, w);
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(go), "l"(w + 1) : "memory");
+        } else {
+            unsigned long long v;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(go) : "memory");
+            } while (v < w + 1);
+        }
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long max_windows) {
@@ -1691,7 +1780,9 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
                 tc = __ldcg(&A.rcin_tail[(size_t)cur * P.NR + r]);
                 tk = __ldcg(&A.rkin_tail[(size_t)cur * P.NR + r]);
             }
-            if (tc | tk | (unsigned)(ws < te_bits)) {
+            unsigned xany = 0;
+            if (X.world > 1) xany = __ldcg(&A.xmask[(size_t)cur * P.NR + r]) != 0ULL;
+            if (tc | tk | xany | (unsigned)(ws < te_bits)) {
                 unsigned pos = lcap - 1 - atomicAdd(&s_nr, 1u);
                 s_list[pos] = r;
                 s_tails[pos] = (tc << 16) | (tk & 0xFFFFu);
@@ -1726,12 +1817,10 @@ __global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArra
         // (4) close the window
         long long c2 = clock64();
         nbar++;
-        grid_barrier(&A.counters[29], (bar0 + nbar) * gridDim.x);
-        if (X.world > 1) {  // exchange minima / completion flags with the other GPUs, then release the local blocks
-            if (blockIdx.x == 0 && tid == 0) peer_window_close(A, X, w);
-            nbar++;
+        if (X.world > 1)
+            grid_barrier_peers(A, X, w, &A.counters[29], (bar0 + nbar) * gridDim.x, &A.counters[30]);
+        else
             grid_barrier(&A.counters[29], (bar0 + nbar) * gridDim.x);
-        }
         long long c3 = clock64();
         t_scan += c1 - c0;
         t_proc += c2 - c1;
@@ -1945,6 +2034,21 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     off = align256(off + 2 * NR * sizeof(unsigned));
     size_t o_rkt = off;
     off = align256(off + 2 * NR * sizeof(unsigned));
+    size_t o_xc = off, o_xk = off, o_xn = off, o_xm = off;
+    if (world > 1) {  // lanes of the global links (only sharded runs use them)
+        if (P.h > 64) {
+            snprintf(dev->error, sizeof dev->error, "sharded runs support at most 64 global ports per router (have %d)", P.h);
+            return 1;
+        }
+        const size_t lanes = 2 * NR * (size_t)P.h;
+        off = align256(off + lanes * DFD_XLANE_CAP * sizeof(ChunkRec));
+        o_xk = off;
+        off = align256(off + lanes * DFD_XLANE_CAP * sizeof(CreditRec));
+        o_xn = off;
+        off = align256(off + lanes * sizeof(unsigned));
+        o_xm = off;
+        off = align256(off + 2 * NR * sizeof(unsigned long long));
+    }
     size_t o_ac = off;
     off = align256(off + NT * sizeof(unsigned));
     size_t o_af = off;
@@ -1959,6 +2063,39 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     A.rkin = (CreditRec*)(xr + o_rkin);
     A.rcin_tail = (unsigned*)(xr + o_rct);
     A.rkin_tail = (unsigned*)(xr + o_rkt);
+    if (world > 1) {
+        A.xc = (ChunkRec*)(xr + o_xc);
+        A.xk = (CreditRec*)(xr + o_xk);
+        A.xcnt = (unsigned*)(xr + o_xn);
+        A.xmask = (unsigned long long*)(xr + o_xm);
+        dev->x_zero_off = o_xn;  // counts and masks are cleared at reset
+        dev->x_zero_bytes = o_ac - o_xn;
+        if (dalloc(dev, &A.xsend, NR * (size_t)P.h)) return 1;
+        // far-end port of every global link: the j-th link from s to r pairs with the j-th link from r to s
+        std::vector<int> grev((size_t)NR * P.h, 0);
+        for (size_t sr = 0; sr < NR; sr++)
+            for (int k = 0; k < P.h; k++) {
+                int r = T.gdest[sr * P.h + k];
+                if (r < 0) continue;
+                int j = 0;
+                for (int k2 = 0; k2 < k; k2++) j += T.gdest[sr * P.h + k2] == r;
+                int kp = -1;
+                for (int k2 = 0; k2 < P.h; k2++)
+                    if (T.gdest[(size_t)r * P.h + k2] == (int)sr && j-- == 0) {
+                        kp = k2;
+                        break;
+                    }
+                if (kp < 0) {
+                    snprintf(dev->error, sizeof dev->error, "global link %zu -> %d has no reverse link: sharded runs need symmetric global connections", sr, r);
+                    return 1;
+                }
+                grev[sr * P.h + k] = kp;
+            }
+        int* d_grev = nullptr;
+        if (dalloc(dev, &d_grev, grev.size())) return 1;
+        CK(cudaMemcpy(d_grev, grev.data(), grev.size() * sizeof(int), cudaMemcpyHostToDevice));
+        A.grev = d_grev;
+    }
     A.ack_count = (unsigned*)(xr + o_ac);
     A.ack_first = (unsigned long long*)(xr + o_af);
     A.ack_last = (unsigned long long*)(xr + o_al);
@@ -2068,7 +2205,11 @@ int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st
 
 int dfd_device_reset(DfdDevice* dev, cudaStream_t st) {
     int blocks = dev->num_sms * 8;
-    CK(cudaMemsetAsync(dev->xregion, 0, sizeof(DfdSync), st));
+    CK(cudaMemsetAsync(dev->xregion, 0xFF, sizeof(DfdSync), st));  // every slot DFD_SYNC_EMPTY
+    if (dev->X.world > 1) {
+        CK(cudaMemsetAsync(dev->xregion + dev->x_zero_off, 0, dev->x_zero_bytes, st));
+        CK(cudaMemsetAsync(dev->A.xsend, 0, sizeof(uint2) * (size_t)dev->P.NR * dev->P.h, st));
+    }
     dfd_init_kernel<<<blocks, 256, 0, st>>>(dev->P, dev->A, dev->seeds);
     CK(cudaGetLastError());
     return 0;

@@ -34,6 +34,7 @@ struct DfdDevice {
     DfdPeers X;
     char* xregion = nullptr;
     size_t xregion_bytes = 0;
+    size_t x_zero_off = 0, x_zero_bytes = 0;  // lane counts + masks inside the exchange region (sharded runs)
     std::vector<void*> ipc_opened;
     std::vector<void*> allocs;
     size_t bytes_allocated = 0, topo_bytes = 0;

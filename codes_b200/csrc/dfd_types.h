@@ -286,6 +286,13 @@ struct DfdArrays {
     unsigned* efree;             // [NR][rheap_cap]   stack of free wheel entries
     unsigned* wheel;             // [NR][wheel_nb]    bucket heads
     unsigned long long* wbits;   // [NR][wheel_nb/64] non-empty-bucket bitmap
+    // cross-GPU global links (world > 1): one single-writer lane per (router, global port) and window parity
+    ChunkRec* xc;                // [2][NR][h][DFD_XLANE_CAP]
+    CreditRec* xk;               // [2][NR][h][DFD_XLANE_CAP]
+    unsigned* xcnt;              // [2][NR][h]  chunks | credits << 16 written into the lane this window
+    unsigned long long* xmask;   // [2][NR]     bit k: lane k holds records
+    uint2* xsend;                // [NR][h]     sender side: {window stamp, packed counts} of the lane behind my port
+    const int* grev;             // [NR][h]     far-end global-port index of each global link
     ChunkRec* rcin;       // [NR][rcin_cap]
     CreditRec* rkin;      // [NR][rkin_cap]
     unsigned* rcin_tail;  // [NR]
@@ -309,11 +316,15 @@ struct DfdArrays {
 // (written straight into the owner's router inbox through a CUDA-IPC mapping of its exchange region) and the
 // svr->svr ACK statistics.  One window = local grid barrier, flag + minimum exchange over NVLink, local barrier.
 #define DFD_MAX_RANKS 8
-struct DfdSync {                                   // lives at the start of every rank's exchange region
-    unsigned long long flag[DFD_MAX_RANKS];        // flag[k]: number of windows rank k has closed
-    unsigned long long mins[3][DFD_MAX_RANKS];     // mins[w%3][k]: rank k's earliest pending timestamp for window w
-    unsigned long long err[DFD_MAX_RANKS];         // err[k]: device error code raised on rank k
+enum { DFD_XLANE_CAP = 8 };  // records one link can carry per window and direction (chunks and credits each)
+// lives at the start of every rank's exchange region.  mins[w%3][k]: rank k's earliest pending timestamp for
+// window w, written by rank k when it closes window w-1; DFD_SYNC_EMPTY until then, DFD_SYNC_FAILED if rank k
+// raised a device error.
+struct DfdSync {
+    unsigned long long mins[3][DFD_MAX_RANKS];
 };
+#define DFD_SYNC_EMPTY 0xFFFFFFFFFFFFFFFFULL
+#define DFD_SYNC_FAILED 0xFFFFFFFFFFFFFFFEULL
 struct DfdPeers {
     int rank, world;
     int grp_lo[DFD_MAX_RANKS + 1];
