@@ -29,7 +29,7 @@
 
 #define INF_BITS 0x7FF0000000000000ULL
 #define NIL 0xFFFFFFFFu
-#define DFD_BLOCK 128
+#define DFD_BLOCK 512
 
 __device__ __forceinline__ double bits2d(unsigned long long b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ unsigned long long d2bits(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -45,15 +45,28 @@ struct Ctx {
     int cur, nxt;
     unsigned widx;
     bool remote_writes;  // this thread wrote into another rank's memory during the window
+#ifdef DFD_PROFILE
+    long long pst;
+#endif
     unsigned* ev;  // per-block event counters by type (shared memory)
 };
 #define COUNT_EV(c, t) atomicAdd(&(c).ev[t], 1u)
 #ifdef DFD_PROFILE
 #define PROF_T0() long long prof_t0 = clock64()
 #define PROF_ADD(c, t) atomicAdd(&(c).A->counters[32 + (t)], (unsigned long long)(clock64() - prof_t0))
+// fine-grained stamps inside the R_ARRIVE path: counters[58 + k] accumulates the cycles since the previous stamp
+#define PSTAMP0(c) (c).pst = clock64()
+#define PSTAMP(c, k)                                                                     \
+    do {                                                                                 \
+        long long _t = clock64();                                                        \
+        atomicAdd(&(c).A->counters[58 + (k)], (unsigned long long)(_t - (c).pst));       \
+        (c).pst = clock64();                                                             \
+    } while (0)
 #else
 #define PROF_T0()
 #define PROF_ADD(c, t)
+#define PSTAMP0(c)
+#define PSTAMP(c, k)
 #endif
 
 __device__ __forceinline__ void set_error(const DfdArrays& A, unsigned code, unsigned long long info) {
@@ -849,6 +862,10 @@ struct RCtx {
     PortState* port;
     PortQ* pq;
     PoolSlot* pool;
+    // one pending event that is due in this window stays in registers instead of going through the wheel (the
+    // R_SEND that follows an arrival at the same timestamp, a credit drained in the window it is due in)
+    double hot_ts;
+    unsigned hot_src, hot_seq, hot_ref;  // hot_ref == 0: empty
     unsigned* pfree;            // stack of free pool-slot indices
     unsigned* efree;            // stack of free wheel-entry indices
     PendEnt* pent;              // wheel entries
@@ -860,9 +877,39 @@ struct RCtx {
 // Pending events of a router: timing wheel, bucket width = one lookahead window (see PendEnt).
 __device__ __forceinline__ long long wheel_bucket(const DfdParams& P, double ts) { return (long long)(ts * P.inv_window); }
 
+// earliest timestamp in the first non-empty bucket at or after bucket b0 (bucket index is monotone in the
+// timestamp, so no later bucket can hold an earlier event); +inf when there is none
+__device__ __forceinline__ double rwheel_min_from(Ctx& c, RCtx& R, long long b0) {
+    const DfdParams& P = *c.P;
+    if (R.h->pend_n == 0) return DINF;
+    const unsigned nb = (unsigned)P.wheel_nb, mask = nb - 1, nwords = nb >> 6;
+    unsigned start = (unsigned)b0 & mask;
+    unsigned w = start >> 6;
+    unsigned long long bits = R.wbits[w] & (~0ULL << (start & 63));
+    for (unsigned k = 0; k <= nwords; k++) {
+        if (bits) {
+            unsigned bi = (w << 6) + (unsigned)__ffsll((long long)bits) - 1;
+            double m = DINF;
+            for (unsigned e = R.wheel[bi]; e != NIL; e = R.pent[e].next) m = fmin(m, R.pent[e].ts);
+            return m;
+        }
+        w = (w + 1) & (nwords - 1);
+        bits = R.wbits[w];
+        if (k + 1 == nwords) bits &= ~(~0ULL << (start & 63));  // wrapped around to the first word: the part before start
+    }
+    return DINF;
+}
+
 __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned src, unsigned seq, unsigned ref) {
     const DfdParams& P = *c.P;
     if (ts >= P.ts_end) return;
+    if (R.hot_ref == 0 && ts < c.t_end) {
+        R.hot_ts = ts;
+        R.hot_src = src;
+        R.hot_seq = seq;
+        R.hot_ref = ref;
+        return;
+    }
     long long b = wheel_bucket(P, ts);
     if (R.h->ent_nfree == 0 || b - R.b_beg >= (long long)P.wheel_nb || b < R.b_beg) {
         set_error(*c.A, R.h->ent_nfree == 0 ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE, R.r);
@@ -879,36 +926,49 @@ __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned 
     pe->next = head;
     R.wheel[bi] = e;
     if (head == NIL) R.wbits[bi >> 6] |= 1ULL << (bi & 63);
-    unsigned n = ++R.h->pend_n;
-    if (n > R.h->heap_hwm) R.h->heap_hwm = n;
+    R.h->pend_n++;
+    R.h->wmin = fmin(R.h->wmin, ts);
 }
 
-// earliest pending event with ts < t_end, by (ts, src, seq), searched in the buckets the window overlaps; unlinks
-// it and returns its payload reference (or 0 when nothing is due)
+// earliest pending event with ts < t_end, by (ts, src, seq): the register-held entry or, when the wheel's
+// earliest timestamp says something in it is due, the best entry of the buckets the window overlaps.  Removes
+// it and returns its payload reference (0 when nothing is due).
 __device__ __forceinline__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_out) {
     const DfdParams& P = *c.P;
+    if (!(R.h->wmin < c.t_end)) {  // nothing in the wheel is due
+        unsigned ref = R.hot_ref;
+        *now_out = R.hot_ts;
+        R.hot_ref = 0;
+        return ref;
+    }
     const unsigned mask = (unsigned)(P.wheel_nb - 1);
     const long long b_end = wheel_bucket(P, c.t_end);
     unsigned best = NIL, best_prev = NIL, best_b = 0;
-    double bts = 0.0;
+    double bts = DINF, second = DINF;  // second: earliest timestamp among the scanned entries other than best
     unsigned bsrc = 0, bseq = 0;
-    for (long long b = R.b_beg; b <= b_end; b++) {
+    for (long long b = wheel_bucket(P, R.h->wmin); b <= b_end; b++) {
         unsigned bi = (unsigned)b & mask;
         unsigned prev = NIL;
         for (unsigned e = R.wheel[bi]; e != NIL; prev = e, e = R.pent[e].next) {
             const PendEnt& pe = R.pent[e];
-            if (!(pe.ts < c.t_end)) continue;
             if (best == NIL || key_less(pe.ts, pe.src, pe.seq, bts, bsrc, bseq)) {
+                second = bts;
                 best = e;
                 best_prev = prev;
                 best_b = bi;
                 bts = pe.ts;
                 bsrc = pe.src;
                 bseq = pe.seq;
-            }
+            } else
+                second = fmin(second, pe.ts);
         }
     }
-    if (best == NIL) return 0;
+    if (R.hot_ref && key_less(R.hot_ts, R.hot_src, R.hot_seq, bts, bsrc, bseq)) {
+        unsigned ref = R.hot_ref;
+        *now_out = R.hot_ts;
+        R.hot_ref = 0;
+        return ref;
+    }
     PendEnt* pe = &R.pent[best];
     unsigned nxt = pe->next, ref = pe->ref;
     if (best_prev == NIL) {
@@ -918,31 +978,9 @@ __device__ __forceinline__ unsigned rwheel_pop_due(Ctx& c, RCtx& R, double* now_
         R.pent[best_prev].next = nxt;
     R.efree[R.h->ent_nfree++] = best;
     R.h->pend_n--;
+    R.h->wmin = second < DINF ? second : rwheel_min_from(c, R, b_end + 1);
     *now_out = bts;
     return ref;
-}
-
-// exact timestamp of the earliest pending event: the minimum of the first non-empty bucket at or after the window
-// start (bucket index is monotone in the timestamp, so no later bucket can hold an earlier event)
-__device__ __forceinline__ double rwheel_next_ts(Ctx& c, RCtx& R) {
-    const DfdParams& P = *c.P;
-    if (R.h->pend_n == 0) return DINF;
-    const unsigned nb = (unsigned)P.wheel_nb, mask = nb - 1, nwords = nb >> 6;
-    unsigned start = (unsigned)R.b_beg & mask;
-    unsigned w = start >> 6;
-    unsigned long long bits = R.wbits[w] & (~0ULL << (start & 63));
-    for (unsigned k = 0; k <= nwords; k++) {
-        if (bits) {
-            unsigned bi = (w << 6) + (unsigned)__ffsll((long long)bits) - 1;
-            double m = DINF;
-            for (unsigned e = R.wheel[bi]; e != NIL; e = R.pent[e].next) m = fmin(m, R.pent[e].ts);
-            return m;
-        }
-        w = (w + 1) & (nwords - 1);
-        bits = R.wbits[w];
-        if (k + 1 == nwords) bits &= ~(~0ULL << (start & 63));  // wrapped around to the first word: the part before start
-    }
-    return DINF;
 }
 
 // --- connection queries (DragonflyConnectionManager, dragonfly-network-manager.cxx) ----------------
@@ -1256,6 +1294,7 @@ __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double no
         set_error(A, DFD_ERR_DEAD_END, R.r);
         return;
     }
+    PSTAMP(c, 1);  // chunk loaded + routed
     PortState ps;
     PortQ pq;
     load_vec(ps, &R.port[output_port]);
@@ -1305,7 +1344,9 @@ __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double no
     m.next = NIL;
     int occ = get4(ps.vc_occ, output_chan);
     if (occ + P.chunk_size <= max_vc_size) {
+        PSTAMP(c, 2);  // port state loaded, next stop known
         router_credit_send(c, R, now, in_last_hop, in_prev, in_port, in_vc);
+        PSTAMP(c, 3);  // credit sent
         unsigned tl = get4(pq.pend_tail, output_chan);  // append to pending_msgs[port][vc]
         if (tl == NIL)
             set4(pq.pend_head, output_chan, slot);
@@ -1318,6 +1359,7 @@ __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double no
             rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
             ps.in_send_loop = 1;
         }
+        PSTAMP(c, 4);  // queued + R_SEND scheduled
     } else {
         ps.stalled_chunks++;
         // saved_vc / saved_channel = upstream port / vc: already kept in prev_port / prev_vc
@@ -1530,6 +1572,7 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     R.wheel = &A.wheel[(size_t)r * P.wheel_nb];
     R.wbits = &A.wbits[(size_t)r * (P.wheel_nb >> 6)];
     R.b_beg = c.b_beg;
+    R.hot_ref = 0;
     // drain the inbox filled during the previous window: chunks go to pool slots, keys to the heap
 #ifdef DFD_PROFILE
     long long pd0 = clock64();
@@ -1567,8 +1610,8 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     unsigned prof_nev = 0;
 #endif
     for (;;) {
-        if (R.h->pend_n == 0) break;
         double now;
+        PSTAMP0(c);
         unsigned ref = rwheel_pop_due(c, R, &now);
         if (ref == 0) break;
 #ifdef DFD_PROFILE
@@ -1578,7 +1621,9 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
         PROF_T0();
         if (kind == RK_CHUNK) {
             COUNT_EV(c, EV_R_ARRIVE);
+            PSTAMP(c, 0);  // pop
             router_packet_receive(c, R, now, ref & 0x0FFFFFFFu);
+            PSTAMP(c, 5);  // state written back
             PROF_ADD(c, EV_R_ARRIVE);
         } else if (kind == RK_CREDIT) {
             COUNT_EV(c, EV_R_BUFFER);
@@ -1590,7 +1635,7 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
             PROF_ADD(c, EV_R_SEND);
         }
     }
-    double next_ts = rwheel_next_ts(c, R);
+    double next_ts = hd.wmin;
     A.rh[r] = hd;
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
@@ -1909,6 +1954,7 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdSeedConsts K) {
         seed_stream(h->rng, (unsigned long long)rtr_gid(P, r) * 3 + 0, K);
         h->pool_nfree = (uint32_t)P.rpool_cap;
         h->ent_nfree = (uint32_t)P.rheap_cap;
+        h->wmin = DINF;
         h->gid = rtr_gid(P, r);
         h->lid = (uint16_t)(r % P.a);
         h->grp = (uint16_t)(r / P.a);
@@ -2126,7 +2172,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     // grid: persistent and co-resident (cooperative launch).  The engine is latency-bound (one grid barrier per
     // lookahead window), so LPs are spread thinly: ~DFD_LPS_PER_BLOCK LPs per block until every SM holds
     // blocks_per_sm blocks, after which the per-block slice grows.
-    dev->block = DFD_BLOCK;
+    dev->block = 128;
     if (const char* ev = getenv("DFD_BLOCK_THREADS")) dev->block = std::max(32, std::min(DFD_BLOCK, atoi(ev) / 32 * 32));
     int lps_per_block = 16;
     if (const char* ev = getenv("DFD_LPS_PER_BLOCK")) lps_per_block = std::max(1, atoi(ev));

@@ -1086,6 +1086,10 @@ static void profile_print(dfd_engine* e) {
     const char* kn[4] = {"node", "router", "?", "router+drain"};
     for (int k = 0; k < 4; k++)
         if (cnt[k]) fprintf(stderr, "  slowest activation of the window is a %-12s in %6llu windows: avg %.0f cycles, %.1f events\n", kn[k], cnt[k], sum[k] / cnt[k], sumev[k] / cnt[k]);
+    if (C[4 + 11]) {
+        const char* st[6] = {"pop", "load chunk + route", "load port, next stop", "credit send", "enqueue + schedule R_SEND", "write back"};
+        for (int k = 0; k < 6; k++) fprintf(stderr, "  R_ARRIVE stage %-26s %7.0f cycles\n", st[k], (double)C[58 + k] / C[4 + 11]);
+    }
     if (C[57]) fprintf(stderr, "  drained records %llu, cycles/record %.0f\n", C[57], (double)C[56] / C[57]);
     if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
 }

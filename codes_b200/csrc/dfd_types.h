@@ -146,7 +146,7 @@ struct __attribute__((aligned(16))) RouterHdr {
     uint32_t ent_nfree;  // entries on the free wheel-entry stack
     uint32_t pool_used;
     uint32_t heap_hwm;
-    double pad_f;
+    double wmin;         // exact earliest timestamp among the wheel entries (+inf when the wheel is empty)
     unsigned long long rng_draws;
 };
 
