@@ -284,7 +284,7 @@ def main():
             "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": 2 * args.steps, "clocks": clocks}
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is timed at N=1 only
         import tempfile
         from tests import oracle_util
         if oracle_util.ref_available():

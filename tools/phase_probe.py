@@ -2,6 +2,8 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import codes_b200
+if os.environ.get("DFD_LIB"):  # A/B runs: load another build of the library
+    codes_b200.LIB_PATH = os.environ["DFD_LIB"]
 conf = sys.argv[1]
 opts = dict(kv.split("=") for kv in sys.argv[2:])
 opts = {k: (float(v) if "." in v else int(v)) for k, v in opts.items()}
