@@ -12,8 +12,10 @@ state is re-initialised on the device, then the window kernel runs the event loo
              table upload (H2D) + device init + event loop + statistics download (D2H) + *_final handlers
   roofline   algorithmic bytes (832*sum(N_hop) + 896*N_chunks per run) / kernel time vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the CPU oracle (single-threaded restatement of the reference handlers) on the same workload
---impl reference times that CPU implementation alone (the reference itself needs ROSS + MPI, absent here).
+  cpu_baseline  (N=1) the reference's own handler sources compiled against the sequential shim engine (oracle/_ref,
+             kind "reference"), or the restatement oracle when that binary is absent (kind "port"), single thread,
+             on the same workload
+--impl reference times that CPU implementation alone (the real ROSS + MPI are external and absent here).
 """
 import argparse
 import json

@@ -144,8 +144,7 @@ struct __attribute__((aligned(16))) RouterHdr {
     uint32_t gid;        // codes_mapping gid of this router
     uint16_t lid, grp;   // id inside the group, group id
     uint32_t ent_nfree;  // entries on the free wheel-entry stack
-    uint32_t pool_used;
-    uint32_t heap_hwm;
+    uint32_t pad0, pad1;
     double wmin;         // exact earliest timestamp among the wheel entries (+inf when the wheel is empty)
     unsigned long long rng_draws;
 };
