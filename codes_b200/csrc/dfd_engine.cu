@@ -2288,8 +2288,11 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st) {
     CK(cudaMemcpyAsync(out->ack_first.data(), A.ack_first, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->ack_last.data(), A.ack_last, sizeof(unsigned long long) * P.NT, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost, st));
-    out->winmax.resize(65536);
-    CK(cudaMemcpyAsync(out->winmax.data(), A.winmax, sizeof(unsigned long long) * 65536, cudaMemcpyDeviceToHost, st));
+    out->winmax.clear();
+    if (getenv("DFD_PROFILE_PRINT")) {  // per-window slowest activation, filled by -DDFD_PROFILE builds only
+        out->winmax.resize(65536);
+        CK(cudaMemcpyAsync(out->winmax.data(), A.winmax, sizeof(unsigned long long) * 65536, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     out->d2h_bytes = sizeof(NodeState) * (size_t)P.NT + sizeof(RouterHdr) * (size_t)P.NR + sizeof(PortState) * (size_t)P.NR * P.radix +
                      (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * (size_t)P.NT + sizeof(unsigned long long) * 32;

@@ -13,6 +13,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <chrono>
 #include <map>
 #include <string>
 #include <utility>
@@ -486,7 +487,7 @@ void finalize(dfd_engine* e) {
     const dfd_synthetic_opts& o = e->opts;
     dfd_summary& S = e->sum;
     e->lpio.clear();
-    e->raw.clear();
+    e->raw.clear();  // built on demand (build_raw)
     const unsigned long long* C = e->res.counters;
     S.events = C[0];
     S.windows = C[1];
@@ -522,8 +523,6 @@ void finalize(dfd_engine* e) {
                             o.payload_sz * ns.msg_sent_count, o.payload_sz * ns.msg_recvd_count, e->load * p.svr_link_bandwidth, observed_load,
                             last_recv_ts, observed_load_time);
                 lpio_write(e, "synthetic-stats", rec);
-                e->raw += sfmt("S %d %d %d %d %d %a %a %a %a %a\n", (int)g, ns.msg_sent_count, ns.msg_recvd_count, ns.local_recvd_count,
-                               (int)e->res.ack_count[k], first_recv_ts, last_recv_ts, ns.last_send_ts, ns.sum_server_latency, ns.max_server_latency);
             } else if (off >= p.off_term && off < p.off_term + p.n_term) {
                 unsigned k = rep * p.n_term + (off - p.off_term);
                 const NodeState& s = e->res.node[k];
@@ -568,12 +567,6 @@ void finalize(dfd_engine* e) {
                             s.total_time / s.finished_chunks, s.max_latency, s.min_latency, (long)s.finished_packets,
                             (double)s.total_hops / s.finished_chunks, avg_busy_time);
                 lpio_write(e, "dragonfly-cn-stats", rec);
-                e->raw += sfmt("T %d %d %d %d %llu %ld %ld %ld %a %a %a %a %a %llu %lu %lu %lu %lu %a %a %ld %ld\n", (int)g, s.packet_gen, s.packet_fin,
-                               s.total_gen_size, (unsigned long long)s.total_msg_size, (long)s.finished_msgs, (long)s.finished_chunks,
-                               (long)s.finished_packets, s.total_time, s.total_hops, s.max_latency, s.min_latency, s.busy_time,
-                               (unsigned long long)s.link_traffic, (unsigned long)s.total_chunks, (unsigned long)s.stalled_chunks,
-                               (unsigned long)s.injected_chunks, (unsigned long)s.ejected_chunks, s.send_time, s.recv_time, (long)s.send_count,
-                               (long)s.recv_count);
             } else {
                 unsigned r = rep;
                 const PortState* ps = &e->res.port[(size_t)r * p.radix];
@@ -596,6 +589,39 @@ void finalize(dfd_engine* e) {
                                 (unsigned long long)ps[port].link_traffic, ps[port].busy_time, (unsigned long)ps[port].stalled_chunks);
                 }
                 lpio_write(e, "dragonfly-link-stats", rec);
+            }
+        }
+    }
+}
+
+// raw-lp-stats: the same per-LP statistics as C99 hex floats, for bit-exact comparison in the tests.  Built only
+// when lp_io_flush asks for it: it is not part of the reference's output and costs a third of the final handlers.
+void build_raw(dfd_engine* e) {
+    if (!e->raw.empty()) return;
+    const HostParams& p = e->hp;
+    const unsigned long long INF = 0x7FF0000000000000ULL;
+    for (int rep = 0; rep < p.repetitions; rep++) {
+        for (int off = 0; off < p.lps_per_rep; off++) {
+            unsigned g = (unsigned)rep * p.lps_per_rep + off;
+            if (off >= p.off_svr && off < p.off_svr + p.n_svr) {
+                unsigned k = rep * p.n_svr + (off - p.off_svr);
+                const NodeState& ns = e->res.node[k];
+                double first_recv_ts = e->res.ack_first[k] == INF ? -1.0 : bits_to_double(e->res.ack_first[k]);
+                double last_recv_ts = bits_to_double(e->res.ack_last[k]);
+                e->raw += sfmt("S %d %d %d %d %d %a %a %a %a %a\n", (int)g, ns.msg_sent_count, ns.msg_recvd_count, ns.local_recvd_count,
+                               (int)e->res.ack_count[k], first_recv_ts, last_recv_ts, ns.last_send_ts, ns.sum_server_latency, ns.max_server_latency);
+            } else if (off >= p.off_term && off < p.off_term + p.n_term) {
+                unsigned k = rep * p.n_term + (off - p.off_term);
+                const NodeState& s = e->res.node[k];
+                e->raw += sfmt("T %d %d %d %d %llu %ld %ld %ld %a %a %a %a %a %llu %lu %lu %lu %lu %a %a %ld %ld\n", (int)g, s.packet_gen, s.packet_fin,
+                               s.total_gen_size, (unsigned long long)s.total_msg_size, (long)s.finished_msgs, (long)s.finished_chunks,
+                               (long)s.finished_packets, s.total_time, s.total_hops, s.max_latency, s.min_latency, s.busy_time,
+                               (unsigned long long)s.link_traffic, (unsigned long)s.total_chunks, (unsigned long)s.stalled_chunks,
+                               (unsigned long)s.injected_chunks, (unsigned long)s.ejected_chunks, s.send_time, s.recv_time, (long)s.send_count,
+                               (long)s.recv_count);
+            } else {
+                unsigned r = rep;
+                const PortState* ps = &e->res.port[(size_t)r * p.radix];
                 for (int i = 0; i < p.radix; i++)
                     e->raw += sfmt("R %d %d %lld %a %lu %lu %a\n", (int)g, i, (long long)ps[i].link_traffic, ps[i].busy_time,
                                    (unsigned long)ps[i].stalled_chunks, (unsigned long)ps[i].total_chunks, ps[i].noat);
@@ -1213,14 +1239,27 @@ int dfd_engine_finalize(dfd_engine* e) {
 }
 
 int dfd_tw_run(dfd_engine* e, void* stream) {
+    const bool timing = getenv("DFD_TIMING") != nullptr;  // host wall clock of the three phases on stderr
+    auto t0 = std::chrono::steady_clock::now();
     if (dfd_engine_upload(e, stream)) return 1;
+    if (timing) cudaStreamSynchronize((cudaStream_t)stream);
+    auto t1 = std::chrono::steady_clock::now();
     if (dfd_engine_run(e, stream)) return 1;
-    return dfd_engine_finish(e, stream);
+    if (timing) cudaStreamSynchronize((cudaStream_t)stream);
+    auto t2 = std::chrono::steady_clock::now();
+    int rc = dfd_engine_finish(e, stream);
+    auto t3 = std::chrono::steady_clock::now();
+    if (timing) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "dfd_tw_run: upload+init %.2f ms, event loop %.2f ms, download+final %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    }
+    return rc;
 }
 
 int dfd_lp_io_flush(dfd_engine* e, const char* directory) {
     if (!e->finished) return fail(e, "lp_io_flush: the engine has not finished a run");
     if (mkdir(directory, 0775) != 0 && errno != EEXIST) return fail(e, "cannot create %s: %s", directory, strerror(errno));
+    build_raw(e);
     std::vector<LpioFile> files = e->lpio;
     files.push_back({"raw-lp-stats", e->raw});
     files.push_back({"summary.txt", report_text(e)});
