@@ -1279,6 +1279,8 @@ __device__ __forceinline__ void router_credit_send(Ctx& c, RCtx& R, double now, 
         push_credit_to_router(c, prev_lp, now + P.local_credit, R.gid, seq, port, vc);
 }
 
+__device__ __forceinline__ double router_send_core(Ctx& c, RCtx& R, double now, int output_port, PortState& ps, const PoolSlot& m);
+
 // router_packet_receive dally:7377-7595; the chunk already sits in pool slot `slot`
 __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double now, unsigned slot) {
     const DfdParams& P = *c.P;
@@ -1347,18 +1349,32 @@ __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double no
         PSTAMP(c, 2);  // port state loaded, next stop known
         router_credit_send(c, R, now, in_last_hop, in_prev, in_port, in_vc);
         PSTAMP(c, 3);  // credit sent
+        set4(ps.vc_occ, output_chan, occ + P.chunk_size);
+        if (ps.in_send_loop == 0) {
+            double ts = maxd(ps.noat, now) - now;
+            unsigned send_seq = R.h->seq++;  // the R_SEND event
+            if (ts == 0.0 && R.hot_ref == 0 && R.h->wmin > now) {
+                // The port is idle (so all of its pending lists are empty) and nothing else of this router is due at
+                // or before `now`: the R_SEND scheduled here is the very next event this router executes, and it
+                // sends exactly this chunk.  Run it on the state already in registers: no list append / pop, no
+                // slot write-back, no trip through the pending-event structure.
+                COUNT_EV(c, EV_R_SEND);
+                ps.last_qos_lvl = (uint8_t)output_chan;
+                router_send_core(c, R, now, output_port, ps, m);
+                R.pfree[R.h->pool_nfree++] = slot;
+                store_vec(&R.port[output_port], ps);
+                PSTAMP(c, 4);
+                return;
+            }
+            rheap_push(c, R, now + ts, R.gid, send_seq, (RK_SEND << 28) | (unsigned)output_port);
+            ps.in_send_loop = 1;
+        }
         unsigned tl = get4(pq.pend_tail, output_chan);  // append to pending_msgs[port][vc]
         if (tl == NIL)
             set4(pq.pend_head, output_chan, slot);
         else
             R.pool[tl].next = slot;
         set4(pq.pend_tail, output_chan, slot);
-        set4(ps.vc_occ, output_chan, occ + P.chunk_size);
-        if (ps.in_send_loop == 0) {
-            double ts = maxd(ps.noat, now) - now;
-            rheap_push(c, R, now + ts, R.gid, R.h->seq++, (RK_SEND << 28) | (unsigned)output_port);
-            ps.in_send_loop = 1;
-        }
         PSTAMP(c, 4);  // queued + R_SEND scheduled
     } else {
         ps.stalled_chunks++;
@@ -1378,35 +1394,11 @@ __device__ __forceinline__ void router_packet_receive(Ctx& c, RCtx& R, double no
 }
 
 // router_packet_send dally:7705-8032 (+ get_next_router_vcg :3499-3557)
-__device__ __forceinline__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port) {
+// The part of router_packet_send that moves one chunk out of `output_port`: serialisation delay, the record for the
+// next hop, link statistics.  `m` is the chunk (pool-slot layout); returns the injection time without the router
+// delay (when the port can start its next chunk, relative to now).
+__device__ __forceinline__ double router_send_core(Ctx& c, RCtx& R, double now, int output_port, PortState& ps, const PoolSlot& m) {
     const DfdParams& P = *c.P;
-    PortState ps;
-    PortQ pq;
-    load_vec(ps, &R.port[output_port]);
-    load_vec(pq, &R.pq[output_port]);
-    int output_chan = -1;
-    {
-        int next_rr_vc = (ps.last_qos_lvl + 1) % DFD_NUM_VCS;
-#pragma unroll
-        for (int i = 0; i < DFD_NUM_VCS; i++) {
-            if (output_chan < 0) {
-                if (get4(pq.pend_head, next_rr_vc) != NIL) {
-                    ps.last_qos_lvl = (uint8_t)next_rr_vc;
-                    output_chan = next_rr_vc;
-                } else
-                    next_rr_vc = (next_rr_vc + 1) % DFD_NUM_VCS;
-            }
-        }
-    }
-    if (output_chan < 0) {
-        ps.in_send_loop = 0;
-        if (ps.queued_count && !ps.last_buf_full) ps.last_buf_full = now;
-        store_vec(&R.port[output_port], ps);
-        return;
-    }
-    unsigned slot = get4(pq.pend_head, output_chan);
-    PoolSlot m;
-    load_vec(m, &R.pool[slot]);
     if (ps.last_buf_full) {
         ps.busy_time += (now - ps.last_buf_full);
         ps.last_buf_full = 0.0;
@@ -1465,11 +1457,42 @@ __device__ __forceinline__ void router_packet_send(Ctx& c, RCtx& R, double now, 
     else
         ps.link_traffic += P.chunk_size;
     ps.total_chunks++;
+    ps.noat -= P.router_delay;
+    return injection_ts - P.router_delay;
+}
+
+__device__ __forceinline__ void router_packet_send(Ctx& c, RCtx& R, double now, int output_port) {
+    PortState ps;
+    PortQ pq;
+    load_vec(ps, &R.port[output_port]);
+    load_vec(pq, &R.pq[output_port]);
+    int output_chan = -1;
+    {
+        int next_rr_vc = (ps.last_qos_lvl + 1) % DFD_NUM_VCS;
+#pragma unroll
+        for (int i = 0; i < DFD_NUM_VCS; i++) {
+            if (output_chan < 0) {
+                if (get4(pq.pend_head, next_rr_vc) != NIL) {
+                    ps.last_qos_lvl = (uint8_t)next_rr_vc;
+                    output_chan = next_rr_vc;
+                } else
+                    next_rr_vc = (next_rr_vc + 1) % DFD_NUM_VCS;
+            }
+        }
+    }
+    if (output_chan < 0) {
+        ps.in_send_loop = 0;
+        if (ps.queued_count && !ps.last_buf_full) ps.last_buf_full = now;
+        store_vec(&R.port[output_port], ps);
+        return;
+    }
+    unsigned slot = get4(pq.pend_head, output_chan);
+    PoolSlot m;
+    load_vec(m, &R.pool[slot]);
+    double injection_ts = router_send_core(c, R, now, output_port, ps, m);
     set4(pq.pend_head, output_chan, m.next);  // pop pending_msgs[port][vc]
     if (m.next == NIL) set4(pq.pend_tail, output_chan, NIL);
     R.pfree[R.h->pool_nfree++] = slot;  // free the slot
-    ps.noat -= P.router_delay;
-    injection_ts -= P.router_delay;
     bool more = (pq.pend_head[0] != NIL) | (pq.pend_head[1] != NIL) | (pq.pend_head[2] != NIL) | (pq.pend_head[3] != NIL);
     if (!more)
         ps.in_send_loop = 0;
@@ -1732,9 +1755,13 @@ __device__ __forceinline__ void grid_barrier_peers(const DfdArrays& A, const Dfd
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(DFD_BLOCK) dfd_run_kernel(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long max_windows) {
+// Two instantiations: <128, 2> lets the compiler use up to 255 registers per thread (186 used, nothing spilled) for
+// partitions whose grid fits 2 blocks per SM; <512, 1> caps at 128 registers so that 16 warps per SM stay resident
+// for large partitions.
+template <int MAX_THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(MAX_THREADS, MIN_BLOCKS) dfd_run_kernel(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long max_windows) {
     extern __shared__ unsigned s_list[];  // [lps_per_block]: bit31 = router, low bits = index; then tc/tk halves
-    __shared__ double s_min[DFD_BLOCK / 32];
+    __shared__ double s_min[MAX_THREADS / 32];
     __shared__ unsigned s_ev[EV_NTYPES];
     __shared__ unsigned s_n, s_nr;  // active nodes (list front) / active routers (list back)
     const unsigned tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
@@ -2172,20 +2199,24 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     // grid: persistent and co-resident (cooperative launch).  The engine is latency-bound (one grid barrier per
     // lookahead window), so LPs are spread thinly: ~DFD_LPS_PER_BLOCK LPs per block until every SM holds
     // blocks_per_sm blocks, after which the per-block slice grows.
+    const size_t ownT = dev->X.n1 - dev->X.n0, ownR = dev->X.r1 - dev->X.r0;
     dev->block = 128;
     if (const char* ev = getenv("DFD_BLOCK_THREADS")) dev->block = std::max(32, std::min(DFD_BLOCK, atoi(ev) / 32 * 32));
+    // small partitions are latency-bound with at most 2 blocks per SM: give the compiler the registers
+    bool wide = ownT + ownR <= 12288 && dev->block <= 128;
+    if (const char* ev = getenv("DFD_WIDE_REGS")) wide = atoi(ev) != 0 && dev->block <= 128;
+    dev->kernel = wide ? (const void*)dfd_run_kernel<128, 2> : (const void*)dfd_run_kernel<DFD_BLOCK, 1>;
     int lps_per_block = 16;
     if (const char* ev = getenv("DFD_LPS_PER_BLOCK")) lps_per_block = std::max(1, atoi(ev));
-    const size_t ownT = dev->X.n1 - dev->X.n0, ownR = dev->X.r1 - dev->X.r0;
     size_t want = (ownT + ownR + lps_per_block - 1) / lps_per_block;
     for (int iter = 0; iter < 2; iter++) {
         // dynamic shared memory depends on the slice size, which depends on the grid: settle in two passes
         size_t g = iter == 0 ? std::max<size_t>(1, want) : (size_t)dev->grid;
         size_t ntb = (ownT + g - 1) / g, nrb = (ownR + g - 1) / g;
         dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
-        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
+        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dev->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfd_run_kernel, dev->block, dev->smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(DfdParams, DfdArrays, DfdPeers, unsigned long long))dev->kernel, dev->block, dev->smem));
         if (per_sm < 1) {
             snprintf(dev->error, sizeof dev->error, "run kernel does not fit on an SM (%zu bytes of shared memory)", dev->smem);
             return 1;
@@ -2198,7 +2229,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     {
         size_t g = dev->grid, ntb = (ownT + g - 1) / g, nrb = (ownR + g - 1) / g;
         dev->smem = (ntb + nrb) * 2 * sizeof(unsigned);
-        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dfd_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
+        if (dev->smem > 48 * 1024) CK(cudaFuncSetAttribute(dev->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev->smem));
     }
     return 0;
 }
@@ -2268,7 +2299,7 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windo
             return 1;
         }
     void* args[] = {(void*)&dev->P, (void*)&dev->A, (void*)&dev->X, (void*)&max_windows};
-    CK(cudaLaunchCooperativeKernel((void*)dfd_run_kernel, dim3(dev->grid), dim3(dev->block), args, dev->smem, st));
+    CK(cudaLaunchCooperativeKernel(dev->kernel, dim3(dev->grid), dim3(dev->block), args, dev->smem, st));
     return 0;
 }
 

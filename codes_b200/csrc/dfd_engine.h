@@ -40,6 +40,7 @@ struct DfdDevice {
     size_t bytes_allocated = 0, topo_bytes = 0;
     int num_sms = 0, grid = 0, block = 0, blocks_per_sm = 0;
     size_t smem = 0;
+    const void* kernel = nullptr;  // dfd_run_kernel instantiation in use
     char error[512] = {0};
 };
 
