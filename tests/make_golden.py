@@ -5,7 +5,7 @@ container by the reference-source oracle -- the reference's OWN sources for this
 ROSS/MPI shim (oracle/ref -> oracle/_ref) -- and every file is checked to be byte-identical to the output of the
 restatement oracle (oracle/dfdally_oracle.cpp) before it is written.  They pin (i) the restatement against accidental
 change and (ii) the GPU engine on the GPU box, where /root/reference does not exist.
-Run (in the authoring container):  python -m tests.make_golden"""
+Run (in the authoring container):  python -m tests.make_golden   (and  python -m tests.make_golden --large)"""
 import hashlib
 import json
 import os
@@ -48,5 +48,34 @@ def main():
         print(name, res.events)
 
 
+def large():
+    """~100K-terminal golden (BASELINE configs[3] scale): topology from tools/gen_topology.py 64 2 (a=32, p=16, h=16,
+    g=257 -> 131,584 terminals), uniform traffic, 3 messages per terminal.  Digests only; checked on the GPU box by
+    tests/test_gpu_parity.py::test_131k_matches_golden."""
+    import subprocess
+    import sys
+    with tempfile.TemporaryDirectory() as tmp:
+        net = os.path.join(tmp, "net")
+        subprocess.run([sys.executable, os.path.join(oracle_util.ROOT, "tools", "gen_topology.py"), "64", "2", net, "--name", "big"],
+                       check=True, stdout=subprocess.DEVNULL)
+        conf = os.path.join(net, "big.conf")
+        case = dict(num_messages=3, traffic=1)
+        res = oracle_util.run(conf, lp_io_dir=os.path.join(tmp, "out"), **case)
+        out = oracle_util.read_dir(os.path.join(tmp, "out"))
+        # oracle/_ref does not finish this size in 15 minutes (the reference's set-up is super-linear in the LP count);
+        # the restatement is pinned to it on the 24 smaller cases of tests/test_oracle_cpu.py
+        meta = dict(conf="tools/gen_topology.py 64 2 <dir> --name big", options=case, events=res.events,
+                    generated_by="oracle/dfdally_oracle.cpp (restatement oracle)",
+                    finished_packets=res.finished_packets, total_hops=res.total_hops,
+                    sha256={k: hashlib.sha256(v).hexdigest() for k, v in sorted(out.items())})
+        with open(os.path.join(GOLDEN, "131584_uniform_m3.json"), "w") as f:
+            json.dump(meta, f, indent=1, sort_keys=True)
+        print("131584_uniform_m3", res.events)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--large" in sys.argv:
+        large()
+    else:
+        main()

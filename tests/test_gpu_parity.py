@@ -156,3 +156,53 @@ def test_full_size_properties_1056(tmp_path):
     cn = parse_cn_stats(out["dragonfly-cn-stats"])
     assert sum(r["recvd"] for r in cn) == 2048 * n * msgs
     assert all(r["avg_hops"] <= 4.0 for r in cn)
+
+
+NARROW_CASES = [
+    ("72-m20", CONF72, dict(num_messages=20)),
+    ("72-nearest-group", CONF72, dict(num_messages=10, traffic=3)),
+    ("1056-uniform", CONF1056, dict(num_messages=10)),
+    ("8320-par-nearest-group", CONF8K, dict(num_messages=3, traffic=3)),
+]
+
+
+@pytest.mark.parametrize("name,conf,opts", NARROW_CASES, ids=[c[0] for c in NARROW_CASES])
+def test_large_partition_kernel_matches_oracle(tmp_path, monkeypatch, name, conf, opts):
+    """The window kernel exists in two register budgets; partitions of more than 12,288 LPs get the 128-register
+    instantiation (16 resident warps per SM).  Force it on the small configs the oracle can follow."""
+    monkeypatch.setenv("DFD_WIDE_REGS", "0")
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)
+
+
+def test_131k_matches_golden(tmp_path):
+    """~100K-terminal scale (BASELINE configs[3]: a=32, p=16, h=16, g=257 -> 131,584 terminals, 8,224 routers) on the
+    large-partition kernel: every lp-io file and the hex-float statistics must hash to the committed golden digests
+    (tests/golden/131584_uniform_m3.json, generated by the restatement oracle), plus
+    the size-independent conservation / credit invariants."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_topology.py"), "64", "2", str(tmp_path / "net"), "--name", "big"],
+                   check=True, stdout=subprocess.DEVNULL)
+    gdir = str(tmp_path / "gpu")
+    msgs, n = 3, 131584
+    s = codes_b200.run_synthetic(str(tmp_path / "net" / "big.conf"), lp_io_dir=gdir, num_messages=msgs)
+    assert s.grid_blocks > 296  # the large-partition kernel
+    out = oracle_util.read_dir(gdir)
+    with open(os.path.join(GOLDEN, "131584_uniform_m3.json")) as f:
+        gold = json.load(f)
+    assert s.events == gold["events"] and s.total_hops == gold["total_hops"]
+    for fname, digest in gold["sha256"].items():
+        if fname != "summary.txt":
+            assert hashlib.sha256(out[fname]).hexdigest() == digest, fname
+    assert s.packet_gen == s.packet_fin == n * msgs == s.finished_msgs == s.svr_msgs_recvd
+    assert s.minimal_count == s.finished_chunks and s.nonmin_count == 0
+    links = parse_link_stats(out["dragonfly-link-stats"])
+    stalled_inj = sum(l["stalled"] for l in links if l["st"] == "T")
+    assert s.events == 11 * n * msgs + 3 * s.total_hops + n + stalled_inj
+    assert sum(l["traffic"] for l in links if l["st"] == "T") == 4096 * s.finished_chunks
+    assert sum(l["traffic"] for l in links if l["st"] == "R" and l["dt"] == "T") == 2048 * s.finished_chunks
+    cn = parse_cn_stats(out["dragonfly-cn-stats"])
+    assert sum(r["recvd"] for r in cn) == 2048 * n * msgs
+    assert all(r["avg_hops"] <= 4.0 for r in cn if r["avg_hops"] == r["avg_hops"])  # NaN: a terminal that received nothing
