@@ -1632,6 +1632,10 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
 #ifdef DFD_PROFILE
     unsigned prof_nev = 0;
 #endif
+#ifdef DFD_PROFILE2
+    long long p2_t0 = clock64();
+    unsigned p2_seq = 0, p2_n = 0;
+#endif
     for (;;) {
         double now;
         PSTAMP0(c);
@@ -1641,6 +1645,10 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
         prof_nev++;
 #endif
         unsigned kind = ref >> 28;
+#ifdef DFD_PROFILE2
+        if (p2_n < 10) p2_seq |= kind << (2 * p2_n);
+        p2_n++;
+#endif
         PROF_T0();
         if (kind == RK_CHUNK) {
             COUNT_EV(c, EV_R_ARRIVE);
@@ -1662,6 +1670,13 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
     A.rh[r] = hd;
     A.wake_self[P.NT + r] = d2bits(next_ts);
     c.cand = fmin(c.cand, next_ts);
+#ifdef DFD_PROFILE2
+    {   // slowest activation of the window: cycles (from after the drain) | drained chunks | credits | events | event kinds
+        unsigned long long dt = (unsigned long long)(clock64() - p2_t0);
+        atomicMax(&A.winmax[c.widx & 0xFFFF], (dt << 32) | ((unsigned long long)min(15u, ntail_c) << 28) | ((unsigned long long)min(15u, ntail_k) << 24) |
+                                                  ((unsigned long long)min(15u, p2_n) << 20) | (p2_seq & 0xFFFFFu));
+    }
+#endif
 #ifdef DFD_PROFILE
     {
         unsigned long long dt = (unsigned long long)(clock64() - prof_lp0);

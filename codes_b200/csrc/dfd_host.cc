@@ -13,6 +13,7 @@
 #include <string.h>
 #include <sys/stat.h>
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <string>
@@ -1095,6 +1096,33 @@ static void fill_summary_meta(dfd_engine* e) {
 
 static void profile_print(dfd_engine* e) {
     if (!getenv("DFD_PROFILE_PRINT")) return;
+    if (getenv("DFD_PROFILE2")) {  // -DDFD_PROFILE2 build: which router activations are the slowest of their window
+        std::map<unsigned, std::pair<unsigned long long, double>> pat;
+        unsigned long long nwin = 0;
+        double total = 0;
+        for (unsigned long long v : e->res.winmax) {
+            if (!v) continue;
+            auto& q = pat[(unsigned)(v & 0xFFFFFFFFu)];
+            q.first++;
+            q.second += (double)(v >> 32);
+            total += (double)(v >> 32);
+            nwin++;
+        }
+        std::vector<std::pair<double, unsigned>> order;
+        for (auto& kv : pat) order.push_back({kv.second.second, kv.first});
+        std::sort(order.rbegin(), order.rend());
+        fprintf(stderr, "  slowest router activation per window (cycles after the drain): %llu windows, mean %.0f cycles\n", nwin, total / std::max(1ULL, nwin));
+        for (size_t i = 0; i < order.size() && i < 24; i++) {
+            unsigned k = order[i].second;
+            auto& q = pat[k];
+            char seq[16] = {0};
+            unsigned n = (k >> 20) & 15;
+            for (unsigned j = 0; j < n && j < 10; j++) seq[j] = " ABS"[(k >> (2 * j)) & 3];  // A arrive, B buffer, S send
+            fprintf(stderr, "    drained %2u chunks %2u credits, events %-10s : %6llu windows (%4.1f%% of the cycles), mean %6.0f cycles\n", (k >> 28) & 15, (k >> 24) & 15,
+                    seq, q.first, 100.0 * q.second / total, q.second / q.first);
+        }
+        return;
+    }
     const unsigned long long* C = e->res.counters;
     const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
     for (int i = 0; i < EV_NTYPES; i++)
