@@ -31,7 +31,18 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("cpu:gloo,cuda:nccl")
     ok = True
-    for conf, opts in CASES:
+    cases = list(CASES)
+    # parallel global links between groups (the far-end port pairing of the link lanes), generated on the fly
+    import subprocess
+    gen = os.path.join(tempfile.gettempdir(), "mgpu_check_shapes")
+    if rank == 0:
+        for radix, conns, routing in ((15, 2, "prog-adaptive"), (23, 4, "minimal")):
+            subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), os.path.join(gen, f"r{radix}c{conns}"),
+                            "--name", "t", "--routing", routing], check=True, stdout=subprocess.DEVNULL)
+    dist.barrier()
+    cases.append((os.path.join(gen, "r15c2", "t.conf"), dict(num_messages=4, traffic=3)))
+    cases.append((os.path.join(gen, "r23c4", "t.conf"), dict(num_messages=4)))
+    for conf, opts in cases:
         conf = os.path.join(ROOT, conf)
         with tempfile.TemporaryDirectory() as tmp:
             gdir, odir = os.path.join(tmp, "gpu"), os.path.join(tmp, "oracle")
@@ -43,7 +54,7 @@ def main():
                 g, r = oracle_util.read_dir(gdir), oracle_util.read_dir(odir)
                 same = s.events == o.events and all(g.get(k) == r[k] for k in r)
                 ok &= same
-                print(f"[{dist.get_world_size()} GPUs] {os.path.basename(conf)} {opts}: events {s.events} vs oracle {o.events}, "
+                print(f"[{dist.get_world_size()} GPUs] {os.path.basename(os.path.dirname(conf)) + '/' + os.path.basename(conf)} {opts}: events {s.events} vs oracle {o.events}, "
                       f"windows {s.windows}, {dt:.2f} s -> {'IDENTICAL' if same else 'DIFFERENT'}", flush=True)
                 if not same:
                     for k in r:

@@ -206,3 +206,15 @@ def test_131k_matches_golden(tmp_path):
     cn = parse_cn_stats(out["dragonfly-cn-stats"])
     assert sum(r["recvd"] for r in cn) == 2048 * n * msgs
     assert all(r["avg_hops"] <= 4.0 for r in cn if r["avg_hops"] == r["avg_hops"])  # NaN: a terminal that received nothing
+
+
+from tests.test_oracle_cpu import TOPO_CASES, make_topology
+
+
+@pytest.mark.parametrize("name,radix,conns,routing,opts", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
+def test_engine_matches_oracle_other_shapes(tmp_path, name, radix, conns, routing, opts):
+    """Dragonflies with 2 and 4 parallel global links between groups and router counts that are not powers of two
+    (the candidate lists of the routing functions and the far-end port pairing look different there)."""
+    conf = make_topology(tmp_path, radix, conns, routing)
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)

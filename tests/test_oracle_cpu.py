@@ -277,3 +277,37 @@ def test_restatement_matches_reference_sources_config_variants(tmp_path, ref_ora
     for f in oracle_util.REF_FILES:
         assert r.get(f) == o.get(f), f
     assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
+
+
+# ---- other dragonfly shapes: parallel global links between groups, odd router counts (tools/gen_topology.py) ----
+TOPO_CASES = [
+    # name, radix, links between groups, routing, options       -> a, p=h, groups, terminals
+    ("r11c1-minimal", 11, 1, "minimal", dict(num_messages=5)),                          # 6, 3, 19, 342
+    ("r15c2-minimal", 15, 2, "minimal", dict(num_messages=5)),                          # 8, 4, 17, 544
+    ("r15c2-par-nearest-group", 15, 2, "prog-adaptive", dict(num_messages=4, traffic=3)),
+    ("r19c2-nonminimal", 19, 2, "nonminimal", dict(num_messages=4)),                    # 10, 5, 26, 1300
+    ("r23c4-minimal-nearest-group", 23, 4, "minimal", dict(num_messages=4, traffic=3)),  # 12, 6, 19, 1368
+    ("r23c4-par", 23, 4, "prog-adaptive", dict(num_messages=4, arrival_time=300.0)),
+]
+
+
+def make_topology(tmp_path, radix, conns, routing):
+    import subprocess
+    import sys
+    d = str(tmp_path / "net")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "t", "--routing", routing],
+                   check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(d, "t.conf")
+
+
+@pytest.mark.parametrize("name,radix,conns,routing,opts", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
+def test_restatement_matches_reference_sources_other_shapes(tmp_path, ref_oracle, name, radix, conns, routing, opts):
+    conf = make_topology(tmp_path, radix, conns, routing)
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
+    ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
+    res = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert ev == res.events
+    r, o = oracle_util.read_dir(rdir), oracle_util.read_dir(odir)
+    for f in oracle_util.REF_FILES:
+        assert r.get(f) == o.get(f), f
+    assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
