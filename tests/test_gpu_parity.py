@@ -49,6 +49,11 @@ CASES = [
     ("72-full-chunk", CONF72, dict(num_messages=10, payload_sz=4096)),
     ("72-warmup", CONF72, dict(num_messages=10, warm_up_time=3000.0)),
     ("72-end-time", CONF72, dict(num_messages=20, end_time=12000.0)),  # events past --end are dropped
+    ("72-empty", CONF72, dict(num_messages=0)),                         # nothing to send: one terminating KICKOFF per server
+    ("72-one-byte", CONF72, dict(num_messages=3, payload_sz=1)),
+    ("72-4097-bytes", CONF72, dict(num_messages=2, payload_sz=4097)),   # a full packet + a packet of one byte
+    ("72-burst", CONF72, dict(num_messages=1, arrival_time=1.0)),
+    ("72-early-end", CONF72, dict(num_messages=3, end_time=1500.0)),    # the run ends before the first packet arrives
     ("1056-uniform", CONF1056, dict(num_messages=10)),
     ("1056-nearest-group", CONF1056, dict(num_messages=5, traffic=3)),
     ("8320-par-uniform", CONF8K, dict(num_messages=3)),
