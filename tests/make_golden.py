@@ -48,34 +48,43 @@ def main():
         print(name, res.events)
 
 
-def large():
-    """~100K-terminal golden (BASELINE configs[3] scale): topology from tools/gen_topology.py 64 2 (a=32, p=16, h=16,
-    g=257 -> 131,584 terminals), uniform traffic, 3 messages per terminal.  Digests only; checked on the GPU box by
-    tests/test_gpu_parity.py::test_131k_matches_golden."""
+LARGE = {
+    # name: (radix, links between groups, terminals, messages per terminal)
+    "131584_uniform_m3": (64, 2, 131584, 3),     # a=32, p=16, h=16, g=257   (~20 s of oracle time)
+    "1050624_uniform_m1": (128, 4, 1050624, 1),  # a=64, p=32, h=32, g=513   (~2 min, 1 GB of lp-io text)
+}
+
+
+def large(which):
+    """Large goldens (BASELINE configs[3] / configs[4] scale): topology from tools/gen_topology.py, uniform traffic.
+    Digests only; checked on the GPU box by tests/test_gpu_parity.py::test_large_network_matches_golden."""
     import subprocess
     import sys
+    radix, conns, _, msgs = LARGE[which]
     with tempfile.TemporaryDirectory() as tmp:
         net = os.path.join(tmp, "net")
-        subprocess.run([sys.executable, os.path.join(oracle_util.ROOT, "tools", "gen_topology.py"), "64", "2", net, "--name", "big"],
+        subprocess.run([sys.executable, os.path.join(oracle_util.ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "big"],
                        check=True, stdout=subprocess.DEVNULL)
         conf = os.path.join(net, "big.conf")
-        case = dict(num_messages=3, traffic=1)
+        case = dict(num_messages=msgs, traffic=1)
         res = oracle_util.run(conf, lp_io_dir=os.path.join(tmp, "out"), **case)
         out = oracle_util.read_dir(os.path.join(tmp, "out"))
-        # oracle/_ref does not finish this size in 15 minutes (the reference's set-up is super-linear in the LP count);
-        # the restatement is pinned to it on the 24 smaller cases of tests/test_oracle_cpu.py
-        meta = dict(conf="tools/gen_topology.py 64 2 <dir> --name big", options=case, events=res.events,
+        # oracle/_ref does not finish these sizes in 15 minutes (the reference's set-up is super-linear in the LP count);
+        # the restatement is pinned to it on the smaller cases of tests/test_oracle_cpu.py
+        meta = dict(conf=f"tools/gen_topology.py {radix} {conns} <dir> --name big", options=case, events=res.events,
                     generated_by="oracle/dfdally_oracle.cpp (restatement oracle)",
                     finished_packets=res.finished_packets, total_hops=res.total_hops,
                     sha256={k: hashlib.sha256(v).hexdigest() for k, v in sorted(out.items())})
-        with open(os.path.join(GOLDEN, "131584_uniform_m3.json"), "w") as f:
+        with open(os.path.join(GOLDEN, which + ".json"), "w") as f:
             json.dump(meta, f, indent=1, sort_keys=True)
-        print("131584_uniform_m3", res.events)
+        print(which, res.events)
 
 
 if __name__ == "__main__":
     import sys
     if "--large" in sys.argv:
-        large()
+        for name in LARGE:
+            if len(sys.argv) < 3 or name in sys.argv[2:]:
+                large(name)
     else:
         main()

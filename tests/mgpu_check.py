@@ -60,28 +60,31 @@ def main():
                     for k in r:
                         if g.get(k) != r[k]:
                             print("   differs:", k)
-    # ~100K-terminal scale against the committed digests (tests/golden/131584_uniform_m3.json)
+    # ~100K-terminal (and, with MGPU_CHECK_1M=1, ~1M-terminal) scale against the committed digests (tests/golden/)
     import hashlib
     import json
-    import subprocess
-    net = os.path.join(tempfile.gettempdir(), "mgpu_check_net131k")
-    if rank == 0:
-        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), "64", "2", net, "--name", "big"], check=True,
-                       stdout=subprocess.DEVNULL)
-    dist.barrier()
-    with tempfile.TemporaryDirectory() as tmp:
-        gdir = os.path.join(tmp, "gpu")
-        t0 = time.perf_counter()
-        s = codes_b200.run_sharded(os.path.join(net, "big.conf"), dist, lp_io_dir=gdir if rank == 0 else None, num_messages=3)
-        dt = time.perf_counter() - t0
+    large = [("131584_uniform_m3", 64, 2, 3)]
+    if os.environ.get("MGPU_CHECK_1M"):
+        large.append(("1050624_uniform_m1", 128, 4, 1))
+    for gold_name, radix, conns, msgs in large:
+        net = os.path.join(tempfile.gettempdir(), "mgpu_check_" + gold_name)
         if rank == 0:
-            with open(os.path.join(ROOT, "tests", "golden", "131584_uniform_m3.json")) as f:
-                gold = json.load(f)
-            g = oracle_util.read_dir(gdir)
-            same = s.events == gold["events"] and all(hashlib.sha256(g[k]).hexdigest() == d for k, d in gold["sha256"].items() if k != "summary.txt")
-            ok &= same
-            print(f"[{dist.get_world_size()} GPUs] 131,584 terminals, 3 msgs: events {s.events} vs golden {gold['events']}, windows {s.windows}, "
-                  f"{dt:.2f} s -> {'IDENTICAL' if same else 'DIFFERENT'}", flush=True)
+            subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "big"], check=True,
+                           stdout=subprocess.DEVNULL)
+        dist.barrier()
+        with tempfile.TemporaryDirectory() as tmp:
+            gdir = os.path.join(tmp, "gpu")
+            t0 = time.perf_counter()
+            s = codes_b200.run_sharded(os.path.join(net, "big.conf"), dist, lp_io_dir=gdir if rank == 0 else None, num_messages=msgs)
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                with open(os.path.join(ROOT, "tests", "golden", gold_name + ".json")) as f:
+                    gold = json.load(f)
+                g = oracle_util.read_dir(gdir)
+                same = s.events == gold["events"] and all(hashlib.sha256(g[k]).hexdigest() == d for k, d in gold["sha256"].items() if k != "summary.txt")
+                ok &= same
+                print(f"[{dist.get_world_size()} GPUs] {gold_name}: events {s.events} vs golden {gold['events']}, windows {s.windows}, "
+                      f"{dt:.2f} s -> {'IDENTICAL' if same else 'DIFFERENT'}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

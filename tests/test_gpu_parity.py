@@ -180,22 +180,28 @@ def test_large_partition_kernel_matches_oracle(tmp_path, monkeypatch, name, conf
     assert_identical(s, o, g, r)
 
 
-def test_131k_matches_golden(tmp_path):
-    """~100K-terminal scale (BASELINE configs[3]: a=32, p=16, h=16, g=257 -> 131,584 terminals, 8,224 routers) on the
-    large-partition kernel: every lp-io file and the hex-float statistics must hash to the committed golden digests
-    (tests/golden/131584_uniform_m3.json, generated by the restatement oracle), plus
-    the size-independent conservation / credit invariants."""
+LARGE_GOLDEN = [
+    # golden, radix, links between groups, terminals, messages per terminal
+    ("131584_uniform_m3", 64, 2, 131584, 3),     # BASELINE configs[3] scale: a=32, p=16, h=16, g=257, 8,224 routers
+    ("1050624_uniform_m1", 128, 4, 1050624, 1),  # BASELINE configs[4] scale: a=64, p=32, h=32, g=513, 32,832 routers
+]
+
+
+@pytest.mark.parametrize("gold_name,radix,conns,n,msgs", LARGE_GOLDEN, ids=[g[0] for g in LARGE_GOLDEN])
+def test_large_network_matches_golden(tmp_path, gold_name, radix, conns, n, msgs):
+    """~100K and ~1M terminals on the large-partition kernel: every lp-io file and the hex-float statistics must hash
+    to the committed digests (tests/golden/<name>.json, generated by the restatement oracle with
+    `python -m tests.make_golden --large`), plus the size-independent conservation / credit invariants."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_topology.py"), "64", "2", str(tmp_path / "net"), "--name", "big"],
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_topology.py"), str(radix), str(conns), str(tmp_path / "net"), "--name", "big"],
                    check=True, stdout=subprocess.DEVNULL)
     gdir = str(tmp_path / "gpu")
-    msgs, n = 3, 131584
     s = codes_b200.run_synthetic(str(tmp_path / "net" / "big.conf"), lp_io_dir=gdir, num_messages=msgs)
     assert s.grid_blocks > 296  # the large-partition kernel
     out = oracle_util.read_dir(gdir)
-    with open(os.path.join(GOLDEN, "131584_uniform_m3.json")) as f:
+    with open(os.path.join(GOLDEN, gold_name + ".json")) as f:
         gold = json.load(f)
     assert s.events == gold["events"] and s.total_hops == gold["total_hops"]
     for fname, digest in gold["sha256"].items():
