@@ -49,9 +49,10 @@ def main():
 
 
 LARGE = {
-    # name: (radix, links between groups, terminals, messages per terminal)
-    "131584_uniform_m3": (64, 2, 131584, 3),     # a=32, p=16, h=16, g=257   (~20 s of oracle time)
-    "1050624_uniform_m1": (128, 4, 1050624, 1),  # a=64, p=32, h=32, g=513   (~2 min, 1 GB of lp-io text)
+    # name: (radix, links between groups, terminals, messages per terminal, routing, traffic)
+    "131584_uniform_m3": (64, 2, 131584, 3, "minimal", 1),     # a=32, p=16, h=16, g=257   (~20 s of oracle time)
+    "131584_par_nearest_group_m3": (64, 2, 131584, 3, "prog-adaptive", 3),  # BASELINE configs[3]: PAR, worst-case group permutation
+    "1050624_uniform_m1": (128, 4, 1050624, 1, "minimal", 1),  # a=64, p=32, h=32, g=513   (~2 min, 1 GB of lp-io text)
 }
 
 
@@ -60,18 +61,18 @@ def large(which):
     Digests only; checked on the GPU box by tests/test_gpu_parity.py::test_large_network_matches_golden."""
     import subprocess
     import sys
-    radix, conns, _, msgs = LARGE[which]
+    radix, conns, _, msgs, routing, traffic = LARGE[which]
     with tempfile.TemporaryDirectory() as tmp:
         net = os.path.join(tmp, "net")
-        subprocess.run([sys.executable, os.path.join(oracle_util.ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "big"],
-                       check=True, stdout=subprocess.DEVNULL)
+        subprocess.run([sys.executable, os.path.join(oracle_util.ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "big",
+                        "--routing", routing], check=True, stdout=subprocess.DEVNULL)
         conf = os.path.join(net, "big.conf")
-        case = dict(num_messages=msgs, traffic=1)
+        case = dict(num_messages=msgs, traffic=traffic)
         res = oracle_util.run(conf, lp_io_dir=os.path.join(tmp, "out"), **case)
         out = oracle_util.read_dir(os.path.join(tmp, "out"))
         # oracle/_ref does not finish these sizes in 15 minutes (the reference's set-up is super-linear in the LP count);
         # the restatement is pinned to it on the smaller cases of tests/test_oracle_cpu.py
-        meta = dict(conf=f"tools/gen_topology.py {radix} {conns} <dir> --name big", options=case, events=res.events,
+        meta = dict(conf=f"tools/gen_topology.py {radix} {conns} <dir> --name big --routing {routing}", options=case, events=res.events,
                     generated_by="oracle/dfdally_oracle.cpp (restatement oracle)",
                     finished_packets=res.finished_packets, total_hops=res.total_hops,
                     sha256={k: hashlib.sha256(v).hexdigest() for k, v in sorted(out.items())})
