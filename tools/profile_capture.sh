@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # 3. full capture of the window kernel on the bench workload (second launch: the first one is phase_probe's warm-up run)
 ncu --set full --clock-control none --import-source on -k regex:dfd_run_kernel -s 1 -c 1 -f -o $OUT/window_kernel_1056 python tools/phase_probe.py configs/dfdally-1056.conf num_messages=100 > $OUT/ncu_full.log 2>&1
 # 4. DRAM traffic of the window kernel at scale (8,320- and 1,050,624-terminal configs)
-M=dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum
+M=dram__bytes_read.sum,dram__bytes_write.sum,dram__throughput.avg.pct_of_peak_sustained_elapsed,gpu__time_duration.sum,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active
 ncu --metrics $M --clock-control none -k regex:dfd_run_kernel -s 1 -c 1 --csv --log-file $OUT/dram_8320.csv python tools/phase_probe.py configs/dfdally-8320-par.conf num_messages=50 > $OUT/ncu_8320.log 2>&1
 ncu --metrics $M --clock-control none -k regex:dfd_run_kernel -s 1 -c 1 --csv --log-file $OUT/dram_1m.csv python tools/phase_probe.py /tmp/huge/huge.conf num_messages=10 > $OUT/ncu_1m.log 2>&1
 ls -la $OUT
