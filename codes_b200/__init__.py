@@ -90,6 +90,7 @@ ABI = [
     ("dfd_engine_run", _I, [_P, _P]),
     ("dfd_engine_finish", _I, [_P, _P]),
     ("dfd_tw_run", _I, [_P, _P]),
+    ("dfd_engine_set_ensemble", _I, [_P, _I]),
     ("dfd_engine_set_partition", _I, [_P, _I, _I]),
     ("dfd_engine_ipc_export", _I, [_P, _P]),
     ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
@@ -237,6 +238,10 @@ class Engine:
     def tw_run(self, stream=None):
         self._ck(self._lib.dfd_tw_run(self._h, _P(stream or 0)))
 
+    def set_ensemble(self, simulations):
+        """This engine will share the GPU with simulations-1 others (call before upload)."""
+        self._ck(self._lib.dfd_engine_set_ensemble(self._h, int(simulations)))
+
     # --- group-sharded runs (one process per GPU) ----------------------------------------------------
     def set_partition(self, rank, world):
         self._ck(self._lib.dfd_engine_set_partition(self._h, rank, world))
@@ -288,6 +293,35 @@ def run_synthetic(conf_path, lp_io_dir=None, **opts):
     if rc != 0:
         raise EngineError(err.value.decode(errors="replace"))
     return s
+
+
+def run_ensemble(conf_path, variants, lp_io_dirs=None, streams=None):
+    """Several independent simulations of one network at the same time on ONE GPU (a parameter sweep): `variants` is
+    a list of option dicts (as for run_synthetic), every simulation gets its own engine and CUDA stream, the event
+    loops run concurrently.  Returns the list of Summaries; results are identical to running each variant alone."""
+    import torch
+    k = len(variants)
+    streams = streams or [torch.cuda.Stream() for _ in range(k)]
+    engines = []
+    try:
+        for v, s in zip(variants, streams):
+            e = Engine()
+            engines.append(e)
+            e.setup(conf_path, make_opts(**v))
+            e.set_ensemble(k)
+            e.upload(s.cuda_stream)
+        for e, s in zip(engines, streams):
+            e.run(s.cuda_stream)
+        out = []
+        for i, (e, s) in enumerate(zip(engines, streams)):
+            e.finish(s.cuda_stream)
+            if lp_io_dirs and lp_io_dirs[i]:
+                e.lp_io_flush(lp_io_dirs[i])
+            out.append(e.summary())
+        return out
+    finally:
+        for e in engines:
+            e.close()
 
 
 def run_sharded(conf_path, dist, lp_io_dir=None, stream=None, **opts):

@@ -2064,7 +2064,7 @@ void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X) {
     X->n1 = X->r1 * p;
 }
 
-int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world) {
+int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world, int ensemble) {
     dev->P = P;
     DfdArrays& A = dev->A;
     memset(&A, 0, sizeof A);
@@ -2219,6 +2219,9 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (const char* ev = getenv("DFD_BLOCK_THREADS")) dev->block = std::max(32, std::min(DFD_BLOCK, atoi(ev) / 32 * 32));
     // small partitions are latency-bound with at most 2 blocks per SM: give the compiler the registers
     bool wide = ownT + ownR <= 12288 && dev->block <= 128;
+    // ensemble: this engine shares the GPU with ensemble-1 others -> 1/ensemble of the block slots.  The 186-register
+    // instantiation offers 2 slots per SM, the 128-register one 4: more than 3 simulations take the latter.
+    if (ensemble > 3) wide = false;
     if (const char* ev = getenv("DFD_WIDE_REGS")) wide = atoi(ev) != 0 && dev->block <= 128;
     dev->kernel = wide ? (const void*)dfd_run_kernel<128, 2> : (const void*)dfd_run_kernel<DFD_BLOCK, 1>;
     int lps_per_block = 16;
@@ -2239,6 +2242,10 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
         size_t maxb = (size_t)per_sm * dev->num_sms;
         dev->grid = (int)std::max<size_t>(1, std::min(want, maxb));
         dev->blocks_per_sm = per_sm;
+    }
+    if (ensemble > 1) {
+        int slots = dev->blocks_per_sm * dev->num_sms;
+        dev->grid = std::max(1, std::min(dev->grid, slots / ensemble));
     }
     if (const char* ev = getenv("DFD_GRID")) dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
     {

@@ -45,7 +45,7 @@ struct DfdDevice {
 };
 
 void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X);
-int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world);
+int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world, int ensemble = 1);
 int dfd_device_ipc_export(DfdDevice* dev, void* handle64);
 int dfd_device_ipc_import(DfdDevice* dev, const void* handles, int world);
 int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st);

@@ -183,6 +183,7 @@ struct dfd_engine {
     bool loaded = false, registered = false, mapped = false, configured = false, opts_set = false;
     bool device_ready = false, uploaded = false, finished = false, downloaded = false;
     int rank = 0, world = 1;
+    int ensemble = 1, dev_ensemble = 1;  // engines sharing the GPU (dfd_engine_set_ensemble) / what the device was sized for
     HostParams hp;
     dfd_synthetic_opts opts;
     double mean_interval = 0, load = 0;
@@ -1027,7 +1028,7 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
     if (make_device_params(e, &P)) return 1;
     if (check_in_degree(e)) return 1;
     // the device arrays are kept across runs of the same shape (cudaMalloc/cudaFree dominate a short run otherwise)
-    bool reuse = e->device_ready && e->dev.X.rank == e->rank && e->dev.X.world == e->world && e->world == 1;
+    bool reuse = e->device_ready && e->dev.X.rank == e->rank && e->dev.X.world == e->world && e->world == 1 && e->dev_ensemble == e->ensemble;
     if (reuse) {
         const DfdHostTopo& T = e->topo;
         size_t tb = (T.loc_off.size() + T.loc_port.size() + T.loc_dest.size() + T.gs_port.size() + T.gs_group.size() + T.gdest.size() +
@@ -1050,7 +1051,8 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
         }
         e->dev = DfdDevice();
         seed_consts(&e->dev.seeds);
-        if (dfd_device_create(&e->dev, P, e->topo, e->rank, e->world)) return fail(e, "%s", e->dev.error);
+        if (dfd_device_create(&e->dev, P, e->topo, e->rank, e->world, e->ensemble)) return fail(e, "%s", e->dev.error);
+        e->dev_ensemble = e->ensemble;
         e->device_ready = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
@@ -1263,6 +1265,12 @@ int dfd_engine_finalize(dfd_engine* e) {
     finalize(e);
     fill_summary_meta(e);
     e->finished = true;
+    return 0;
+}
+
+int dfd_engine_set_ensemble(dfd_engine* e, int simulations) {
+    if (e->world > 1 && simulations > 1) return fail(e, "engine_set_ensemble: a group-sharded engine owns its GPU");
+    e->ensemble = simulations > 1 ? simulations : 1;
     return 0;
 }
 

@@ -100,6 +100,12 @@ int dfd_engine_run(dfd_engine* e, void* cuda_stream);
 int dfd_engine_finish(dfd_engine* e, void* cuda_stream);
 /* all of tw_run() in one call with host buffers on both sides */
 int dfd_tw_run(dfd_engine* e, void* cuda_stream);
+/* Ensembles (parameter sweeps: the usual way model-net-synthetic-* is used, one process per parameter point in the
+ * reference).  A network of a few thousand LPs fills a small part of a B200, so several engines can run their event
+ * loops at the same time on different CUDA streams of one GPU.  Call before dfd_engine_upload: `simulations` is the
+ * number of engines that will share the GPU; this engine then sizes its persistent grid to 1/simulations of the
+ * device's co-resident block slots (results do not depend on the grid).  simulations <= 1 restores the default. */
+int dfd_engine_set_ensemble(dfd_engine* e, int simulations);
 
 /* Group-sharded run over several GPUs of one box, one process per GPU (the reference's analogue is
  * codes_mapping()'s block mapping of LPs to MPI ranks, src/util/codes_mapping.c:78-86, with ROSS moving remote
