@@ -84,10 +84,9 @@ def test_partition_api_guards(engine_lib):
             e.export_partition()
 
 
-def test_ensemble_hint_is_for_unsharded_engines():
+def test_ensemble_hint_is_for_unsharded_engines(engine_lib):
     """dfd_engine_set_ensemble: engines that share one GPU; a group-sharded engine owns its GPU."""
     with codes_b200.Engine() as e:
-        e.setup(CONF72, codes_b200.make_opts(num_messages=1))
         e.set_ensemble(8)
         e.set_ensemble(0)  # back to the default
         e.set_partition(1, 2)
