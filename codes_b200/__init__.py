@@ -91,6 +91,7 @@ ABI = [
     ("dfd_engine_finish", _I, [_P, _P]),
     ("dfd_tw_run", _I, [_P, _P]),
     ("dfd_engine_set_ensemble", _I, [_P, _I]),
+    ("dfd_abi_sizes", None, [_P, _P]),
     ("dfd_engine_set_partition", _I, [_P, _I, _I]),
     ("dfd_engine_ipc_export", _I, [_P, _P]),
     ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
@@ -121,6 +122,12 @@ def load_library():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # the two structs that cross the boundary by pointer must mirror this build of the library exactly
+    a, b = ctypes.c_int(0), ctypes.c_int(0)
+    lib.dfd_abi_sizes(ctypes.byref(a), ctypes.byref(b))
+    if (a.value, b.value) != (ctypes.sizeof(Summary), ctypes.sizeof(SyntheticOpts)):
+        raise EngineError(f"{LIB_PATH}: dfd_summary / dfd_synthetic_opts are {a.value} / {b.value} bytes in the library but "
+                          f"{ctypes.sizeof(Summary)} / {ctypes.sizeof(SyntheticOpts)} in this binding: rebuild one of them")
     _lib = lib
     return lib
 

@@ -1268,6 +1268,11 @@ int dfd_engine_finalize(dfd_engine* e) {
     return 0;
 }
 
+void dfd_abi_sizes(int* summary_bytes, int* synthetic_opts_bytes) {
+    if (summary_bytes) *summary_bytes = (int)sizeof(dfd_summary);
+    if (synthetic_opts_bytes) *synthetic_opts_bytes = (int)sizeof(dfd_synthetic_opts);
+}
+
 int dfd_engine_set_ensemble(dfd_engine* e, int simulations) {
     if (e->world > 1 && simulations > 1) return fail(e, "engine_set_ensemble: a group-sharded engine owns its GPU");
     e->ensemble = simulations > 1 ? simulations : 1;

@@ -137,6 +137,9 @@ int dfd_run_synthetic(const char* conf_path, const dfd_synthetic_opts* opts, con
 /* small pure helpers exported for known-answer tests */
 double dfd_bytes_to_ns(unsigned long long bytes, double gib_per_s); /* dally:1588-1599 */
 int dfd_cuda_device_count(void);
+/* sizeof(dfd_summary) / sizeof(dfd_synthetic_opts) of this build: lets a foreign-language binding (ctypes, cgo ...)
+ * check its mirror of the two structs before it passes pointers to them */
+void dfd_abi_sizes(int* summary_bytes, int* synthetic_opts_bytes);
 
 #ifdef __cplusplus
 }
