@@ -912,7 +912,11 @@ __device__ __forceinline__ void rheap_push(Ctx& c, RCtx& R, double ts, unsigned 
     }
     long long b = wheel_bucket(P, ts);
     if (R.h->ent_nfree == 0 || b - R.b_beg >= (long long)P.wheel_nb || b < R.b_beg) {
-        set_error(*c.A, R.h->ent_nfree == 0 ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE, R.r);
+        // info: router | (bucket distance from the window start, clamped to +-2^23) << 32 | event kind << 60
+        long long dist = b - R.b_beg;
+        dist = dist > 8388607 ? 8388607 : dist < -8388607 ? -8388607 : dist;
+        set_error(*c.A, R.h->ent_nfree == 0 ? DFD_ERR_HEAP_OVERFLOW : DFD_ERR_WHEEL_RANGE,
+                  (unsigned long long)R.r | ((unsigned long long)(dist & 0xFFFFFF) << 32) | ((unsigned long long)(ref >> 28) << 60));
         return;
     }
     unsigned e = R.efree[--R.h->ent_nfree];

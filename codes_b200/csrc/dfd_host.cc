@@ -973,7 +973,11 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
         double maxbw_inj = std::max(h_bytes_to_ns(p.chunk_size, p.cn_bandwidth), std::max(h_bytes_to_ns(p.chunk_size, p.local_bandwidth), h_bytes_to_ns(p.chunk_size, p.global_bandwidth)));
         double maxdelay = std::max(p.cn_delay, std::max(p.local_delay, p.global_delay));
         double maxcredit = std::max(p.cn_credit_delay, std::max(p.local_credit_delay, p.global_credit_delay));
-        double span = std::max(2.0 * maxbw_inj + p.router_delay + maxdelay, maxcredit) + 2.0 * L;
+        // A terminal may start a T_SEND while its link is still busy (packet_generate schedules it at +0 whenever the
+        // send loop is idle, dally:5749-5760), so terminal_available_time runs ahead of the clock by up to one
+        // injection time per chunk the VC can hold: the arrival at the first router lies that far in the future.
+        double term_ahead = (double)cn_chunks * h_bytes_to_ns(p.chunk_size, p.cn_bandwidth) + h_bytes_to_ns(p.chunk_size, p.cn_bandwidth) + p.cn_delay;
+        double span = std::max(std::max(2.0 * maxbw_inj + p.router_delay + maxdelay, term_ahead), maxcredit) + 2.0 * L;
         const double bucket = 4.0 * L;  // bucket width: a window overlaps at most two buckets; 4x fewer heads to keep warm
         double nb = span / bucket + 8.0;
         if (nb > 1048576.0) return fail(e, "the ratio of the largest link delay (%g ns) to the lookahead window (%g ns) is too large for the timing wheel; set an explicit credit_delay", span, L);

@@ -831,6 +831,7 @@ public:
         Event& e = pool[idx];
         e = Event();
         e.ts = now + offset;
+        if (debug_maxoff && type < 32 && offset > maxoff[type]) maxoff[type] = offset;
         e.src = cur_lp;
         e.seq = seq[cur_lp]++;
         e.dst = (uint32_t)dst;
@@ -839,6 +840,8 @@ public:
         return e;
     }
     uint32_t pending_idx = 0;
+    bool debug_maxoff = getenv("DFD_ORACLE_MAXOFF") != nullptr;  // largest (timestamp - now) per event type, printed at the end
+    double maxoff[32] = {0};
     void ev_send() {
         Event& e = pool[pending_idx];
         if (e.ts >= ts_end) {  // events at/after the end barrier are never executed
@@ -1734,6 +1737,9 @@ public:
             sum.last_event_ts = now;
             dispatch(ev);
         }
+        if (debug_maxoff)
+            for (int t = 0; t < 32; t++)
+                if (maxoff[t] > 0) fprintf(stderr, "oracle: event type %d: largest (timestamp - now) = %.3f ns\n", t, maxoff[t]);
     }
 
     void lp_io_write(const std::string& id, const std::string& data) {  // lp-io.c:39-100

@@ -251,3 +251,30 @@ def test_ensemble_matches_solo_runs(tmp_path):
         assert sums[i].events == s.events and sums[i].total_hops == s.total_hops
         assert oracle_util.read_dir(dirs[i]) == oracle_util.read_dir(solo), i
         assert sums[i].grid_blocks * len(variants) <= 4 * sums[i].num_sms  # all members are co-resident
+
+
+def test_terminal_runs_ahead_of_its_link(tmp_path):
+    """Found by tools/fuzz_parity.py: small chunks and a deep terminal VC let terminal_available_time run 32 injection
+    times ahead of the clock (packet_generate starts T_SEND at +0 whenever the send loop is idle, dally:5749-5760),
+    so chunk arrivals lie 3.8 us in the future -- the router timing wheel has to span that."""
+    import subprocess
+    import sys
+    net = str(tmp_path / "net")
+    cmd = [sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "gen_topology.py"), "11", "1", net,
+           "--name", "t", "--chunk-size", "256", "--packet-size", "256"]
+    for kv in ("local_vc_size=2048", "global_vc_size=2048", "cn_vc_size=8192", "local_bandwidth=12.5", "global_bandwidth=4.7", "cn_bandwidth=2.0"):
+        cmd += ["--param", kv]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    s, o, g, r = run_both(tmp_path, os.path.join(net, "t.conf"), num_messages=7, payload_sz=9000, arrival_time=1000.0)
+    assert_identical(s, o, g, r)
+
+
+def test_random_configurations_match_oracle():
+    """A slice of the seeded campaign of tools/fuzz_parity.py on the GPU (engine vs oracle, every file byte for byte)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "gpu", "--cases", "40", "--seed", "11"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "40 cases" in r.stdout and "0 mismatches" in r.stdout

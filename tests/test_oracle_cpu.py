@@ -316,3 +316,15 @@ def test_restatement_matches_reference_sources_other_shapes(tmp_path, ref_oracle
     for f in oracle_util.REF_FILES:
         assert r.get(f) == o.get(f), f
     assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
+
+
+def test_random_configurations_match_reference_sources(ref_oracle):
+    """A slice of the seeded campaign of tools/fuzz_parity.py (random shapes, routing, chunk / packet / VC sizes,
+    bandwidths, delays, traffic, payloads, loads): restatement vs reference sources, every lp-io file byte for byte.
+    The full campaigns (310 cases here, 400 on the GPU) are run with the tool itself."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "ref", "--cases", "20", "--seed", "3"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "20 cases" in r.stdout and "0 mismatches" in r.stdout

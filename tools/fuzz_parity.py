@@ -1,0 +1,131 @@
+#!/usr/bin/env python3
+"""Randomised parity campaign (seeded, reproducible): random PARAMS / driver options on small generated dragonflies.
+
+  python tools/fuzz_parity.py ref  [--cases N] [--seed S]   restatement oracle vs oracle/_ref (reference sources)  -- CPU
+  python tools/fuzz_parity.py gpu  [--cases N] [--seed S]   CUDA engine vs restatement oracle                      -- GPU box
+
+Every case compares all lp-io files (and, on the GPU, the hex-float raw statistics) byte for byte.  A case whose
+configuration the reference itself rejects is skipped when both sides reject it."""
+import argparse
+import os
+import random
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests import oracle_util  # noqa: E402
+
+SHAPES = [(7, 1), (11, 1), (11, 2), (15, 1), (15, 2), (19, 2), (23, 4)]
+
+
+def make_case(rng):
+    radix, conns = rng.choice(SHAPES)
+    routing = rng.choice(["minimal", "minimal", "nonminimal", "prog-adaptive", "prog-adaptive"])
+    chunk = rng.choice([256, 512, 1024, 2048, 4096])
+    packet = chunk * rng.choice([1, 1, 2, 4])
+    vc_chunks = rng.choice([1, 2, 4, 8])
+    params = dict(chunk_size=chunk, packet_size=packet,
+                  local_vc_size=chunk * vc_chunks * rng.choice([1, 2]), global_vc_size=chunk * vc_chunks * rng.choice([1, 2]),
+                  cn_vc_size=chunk * vc_chunks * rng.choice([1, 2, 4]),
+                  local_bandwidth=rng.choice(["2.0", "5.25", "12.5"]), global_bandwidth=rng.choice(["2.0", "4.7", "12.5"]),
+                  cn_bandwidth=rng.choice(["2.0", "8.0", "16.0"]))
+    if rng.random() < 0.3:
+        params["router_delay"] = rng.choice(["0", "50", "300"])
+    if rng.random() < 0.3:
+        params["credit_delay"] = rng.choice(["10", "50", "100"])
+    if routing == "prog-adaptive":
+        if rng.random() < 0.5:
+            params["adaptive_threshold"] = str(rng.choice([0, chunk, 4 * chunk]))
+        if rng.random() < 0.5:
+            params["route_scoring_metric"] = rng.choice(["alpha", "delta"])
+    opts = dict(traffic=rng.choice([1, 1, 2, 3, 4, 5]), num_messages=rng.randint(1, 8),
+                payload_sz=rng.choice([1, 8, 200, 1024, 2048, 3000, 4096, 4097, 9000]))
+    if rng.random() < 0.5:
+        opts["arrival_time"] = rng.choice([50.0, 200.0, 1000.0, 5000.0])
+    elif rng.random() < 0.3:
+        opts["load_per_svr"] = rng.choice([0.2, 0.5, 0.9])
+    if rng.random() < 0.2:
+        opts["warm_up_time"] = rng.choice([500.0, 3000.0])
+    if rng.random() < 0.15:
+        opts["end_time"] = rng.choice([4000.0, 20000.0])
+    return radix, conns, routing, params, opts
+
+
+def write_conf(tmp, radix, conns, routing, params):
+    net = os.path.join(tmp, "net")
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "t", "--routing", routing,
+           "--chunk-size", str(params["chunk_size"]), "--packet-size", str(params["packet_size"])]
+    for k, v in params.items():
+        if k not in ("chunk_size", "packet_size"):
+            cmd += ["--param", f"{k}={v}"]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(net, "t.conf")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["ref", "gpu"])
+    ap.add_argument("--cases", type=int, default=100)
+    ap.add_argument("--seed", type=int, default=1)
+    args = ap.parse_args()
+    rng = random.Random(args.seed)
+    oracle_util.load()
+    if args.mode == "gpu":
+        import codes_b200
+    bad = skipped = 0
+    for i in range(args.cases):
+        radix, conns, routing, params, opts = make_case(rng)
+        tag = f"case {i}: shape {radix}/{conns} {routing} {params} {opts}"
+        with tempfile.TemporaryDirectory() as tmp:
+            conf = write_conf(tmp, radix, conns, routing, params)
+            try:
+                res = oracle_util.run(conf, lp_io_dir=os.path.join(tmp, "o"), **opts)
+                o = oracle_util.read_dir(os.path.join(tmp, "o"))
+                oerr = None
+            except oracle_util.OracleError as ex:
+                oerr = str(ex)
+            if args.mode == "ref":
+                try:
+                    ev, _, _ = oracle_util.run_ref(conf, os.path.join(tmp, "r"), **opts)
+                    r = oracle_util.read_dir(os.path.join(tmp, "r"))
+                    rerr = None
+                except Exception as ex:  # the reference aborted (tw_error / assert)
+                    rerr = str(ex)[:200]
+                if oerr or rerr:
+                    if oerr and rerr:
+                        skipped += 1
+                        continue
+                    print("MISMATCH (one side rejected)", tag, "| oracle:", oerr, "| ref:", rerr, flush=True)
+                    bad += 1
+                    continue
+                diffs = [k for k in oracle_util.REF_FILES if r.get(k) != o.get(k)]
+                if ev != res.events or diffs:
+                    print("MISMATCH", tag, "events", ev, res.events, diffs, flush=True)
+                    bad += 1
+            else:
+                try:
+                    s = codes_b200.run_synthetic(conf, lp_io_dir=os.path.join(tmp, "g"), **opts)
+                    g = oracle_util.read_dir(os.path.join(tmp, "g"))
+                    gerr = None
+                except codes_b200.EngineError as ex:
+                    gerr = str(ex)
+                if oerr or gerr:
+                    if oerr and gerr:
+                        skipped += 1
+                        continue
+                    print("MISMATCH (one side rejected)", tag, "| oracle:", oerr, "| gpu:", gerr, flush=True)
+                    bad += 1
+                    continue
+                diffs = [k for k in o if g.get(k) != o[k]]
+                if s.events != res.events or diffs:
+                    print("MISMATCH", tag, "events", s.events, res.events, diffs, flush=True)
+                    bad += 1
+    print(f"{args.mode}: {args.cases} cases, {skipped} rejected by both sides, {bad} mismatches")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,12 +103,23 @@ def write_config(out_dir, name, radix, conns, routing="minimal", packet_size=409
     for k, v in ex.items():
         extra_lines += f'   {k}="{v}";\n'
     conf = os.path.join(out_dir, f"{name}.conf")
+    # an extra parameter that the template already sets replaces the template's value (a key never appears twice)
+    overrides = {}
+    for key, arg in (("local_vc_size", "local_vc"), ("global_vc_size", "global_vc"), ("cn_vc_size", "cn_vc")):
+        if key in ex:
+            overrides[arg] = ex.pop(key)
+    local_vc, global_vc, cn_vc = (overrides.get("local_vc", local_vc), overrides.get("global_vc", global_vc), overrides.get("cn_vc", cn_vc))
+    bws = {k: ex.pop(k) for k in ("local_bandwidth", "global_bandwidth", "cn_bandwidth") if k in ex}
+    extra_lines = "".join(f'   {k}="{v}";\n' for k, v in ex.items())
     with open(conf, "w") as f:
         # link files are written relative to the .conf (resolved against its directory)
-        f.write(CONF_TEMPLATE.format(reps=a * g, p=p, a=a, g=g, h=h, packet_size=packet_size,
+        text = CONF_TEMPLATE.format(reps=a * g, p=p, a=a, g=g, h=h, packet_size=packet_size,
                                      chunk_size=chunk_size, local_vc=local_vc, global_vc=global_vc,
                                      cn_vc=cn_vc, bw=bw, intra=os.path.basename(intra),
-                                     inter=os.path.basename(inter), routing=routing, extra=extra_lines))
+                                     inter=os.path.basename(inter), routing=routing, extra=extra_lines)
+        for k, v in bws.items():
+            text = text.replace(f'{k}="{bw}";', f'{k}="{v}";')
+        f.write(text)
     return conf, dict(a=a, p=p, h=h, g=g, routers=a * g, terminals=a * g * p)
 
 
