@@ -1112,6 +1112,47 @@ __device__ __forceinline__ int best_from_k2(const DfdParams& P, const DfdArrays&
     return r_integer(R, 0, 1) == 0 ? p1 : p2;
 }
 
+// dfdally_get_best_from_k_connections dally:1796-1859 for any k: k distinct indices drawn without replacement
+// (dally:1826-1839), polled in ascending index order, best score wins, ties by one more draw.  The reference loops
+// forever when k exceeds the number of connections (its guard is commented out, dally:1822-1823); here that is a
+// device error instead of a hung GPU.
+__device__ int best_from_k(Ctx& c, const DfdParams& P, const DfdArrays& A, RCtx& R, const Cands& cd, int k) {
+    if (cd.n == 0) return -1;
+    if (cd.n == 1) return cand_port(P, A, R, cd, 0);
+    if (k > cd.n || cd.n > 64 || k < 1) {
+        set_error(A, DFD_ERR_DEAD_END, 0x4000000000000000ULL | R.r);
+        return -1;
+    }
+    unsigned long long sel = 0;
+    long long n = cd.n, last = 0;
+    for (int i = 0; i < k; i++) {
+        long long ri = r_integer(R, 0, (n - 1) - i);
+        long long att = (last + ri) % n;
+        while ((sel >> att) & 1ULL) att = (att + 1) % n;
+        sel |= 1ULL << att;
+        last = att;
+    }
+    if (k == 1) return cand_port(P, A, R, cd, (int)last);  // one polled connection: returned without a draw
+    int best_score = 2147483647, nbest = 0;
+    for (unsigned long long m = sel; m; m &= m - 1) {
+        int sc = score_port(P, R, cand_port(P, A, R, cd, __ffsll((long long)m) - 1), false);
+        if (sc < best_score) {
+            best_score = sc;
+            nbest = 1;
+        } else if (sc == best_score)
+            nbest++;
+    }
+    int pick = (int)r_integer(R, 0, nbest - 1);
+    for (unsigned long long m = sel; m; m &= m - 1) {
+        int port = cand_port(P, A, R, cd, __ffsll((long long)m) - 1);
+        if (score_port(P, R, port, false) == best_score) {
+            if (pick == 0) return port;
+            pick--;
+        }
+    }
+    return -1;
+}
+
 // dfdally_select_intermediate_group dally:9738-9790
 __device__ __forceinline__ void select_intermediate_group(const DfdParams& P, const DfdArrays& A, RCtx& R, PoolSlot& m) {
     int fg = m.dst_grp;
@@ -1230,11 +1271,11 @@ __device__ __forceinline__ int do_routing(Ctx& c, RCtx& R, PoolSlot& m, int fdes
     Cands nonmins = legal_nonminimal_stops(P, A, R, m);
     int best_min, best_non;
     if (mins.n > 0 && mins.kind == 1)
-        best_min = best_from_k2(P, A, R, mins);
+        best_min = P.global_k_picks == 2 ? best_from_k2(P, A, R, mins) : best_from_k(c, P, A, R, mins, P.global_k_picks);
     else
         best_min = best_from_cands(P, A, R, mins);
     if (nonmins.n > 0 && nonmins.kind == 1)
-        best_non = best_from_k2(P, A, R, nonmins);
+        best_non = P.global_k_picks == 2 ? best_from_k2(P, A, R, nonmins) : best_from_k(c, P, A, R, nonmins, P.global_k_picks);
     else
         best_non = best_from_cands(P, A, R, nonmins);
     int min_score = score_port(P, R, best_min, false);

@@ -309,7 +309,7 @@ int read_params(dfd_engine* e) {
         return fail(e, "Gamma scoring protocol currently non-functional");
     else
         p.scoring = DFD_SCORE_DELTA;
-    if (p.routing == DFD_PROG_ADAPTIVE && p.global_k_picks != 2) return fail(e, "global_k_picks != 2 is not supported by this engine");
+    if (p.routing == DFD_PROG_ADAPTIVE && p.global_k_picks < 1) return fail(e, "global_k_picks must be at least 1");
     if (g.geti("num_groups", &p.num_groups)) return fail(e, "\nnum_groups not specified, Aborting\n");
     if (g.geti("num_routers", &p.num_routers)) return fail(e, "\nnum_routers not specified, Aborting\n");
     if (g.geti("num_cns_per_router", &p.num_cn)) p.num_cn = p.num_routers / 2;

@@ -224,7 +224,7 @@ def test_large_network_matches_golden(tmp_path, gold_name, radix, conns, n, msgs
     assert all(r["avg_hops"] <= max_hops for r in cn if r["avg_hops"] == r["avg_hops"])  # NaN: a terminal that received nothing
 
 
-from tests.test_oracle_cpu import TOPO_CASES, make_topology
+from tests.test_oracle_cpu import TOPO_CASES, TOPO_K_CASES, make_topology
 
 
 @pytest.mark.parametrize("name,radix,conns,routing,opts", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
@@ -278,3 +278,19 @@ def test_random_configurations_match_oracle():
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "40 cases" in r.stdout and "0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("name,radix,conns,k,opts", TOPO_K_CASES, ids=[c[0] for c in TOPO_K_CASES])
+def test_engine_matches_oracle_k_picks(tmp_path, name, radix, conns, k, opts):
+    """global_k_picks other than 2 (dfdally_poll_k_connections dally:1796-1849, sampling without replacement)."""
+    conf = make_topology(tmp_path, radix, conns, "prog-adaptive", global_k_picks=k)
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)
+
+
+def test_k_picks_larger_than_the_link_count_is_an_error_not_a_hang(tmp_path):
+    """The reference spins forever when global_k_picks exceeds the links a router has to one group (its guard is
+    commented out, dally:1822-1823).  The engine reports a device error instead of hanging the GPU."""
+    conf = make_topology(tmp_path, 11, 9, "prog-adaptive", global_k_picks=3)
+    with pytest.raises(codes_b200.EngineError, match="dead end"):
+        codes_b200.run_synthetic(conf, num_messages=8, arrival_time=300.0)

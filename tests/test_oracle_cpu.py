@@ -293,15 +293,26 @@ TOPO_CASES = [
     ("r19c2-nonminimal", 19, 2, "nonminimal", dict(num_messages=4)),                    # 10, 5, 26, 1300
     ("r23c4-minimal-nearest-group", 23, 4, "minimal", dict(num_messages=4, traffic=3)),  # 12, 6, 19, 1368
     ("r23c4-par", 23, 4, "prog-adaptive", dict(num_messages=4, arrival_time=300.0)),
+    # routers with two links to the same group: the k-connection poll of progressive-adaptive routing draws twice
+    ("r11c9-par-two-links-per-group", 11, 9, "prog-adaptive", dict(num_messages=8, arrival_time=300.0)),   # 6, 3, 3 groups, 54
+    ("r15c16-par-two-links-per-group", 15, 16, "prog-adaptive", dict(num_messages=6, traffic=3)),           # 8, 4, 3 groups, 96
+    ("r15c8-nonminimal", 15, 8, "nonminimal", dict(num_messages=6)),                                       # 8, 4, 5 groups, 160
+]
+TOPO_K_CASES = [  # global_k_picks other than the default 2
+    ("r11c9-par-k1", 11, 9, 1, dict(num_messages=8, arrival_time=300.0)),
+    ("r15c8-par-k3", 15, 8, 3, dict(num_messages=6, arrival_time=300.0)),
+    ("r11c6-par-k3", 11, 6, 3, dict(num_messages=6, traffic=3)),
 ]
 
 
-def make_topology(tmp_path, radix, conns, routing):
+def make_topology(tmp_path, radix, conns, routing, **params):
     import subprocess
     import sys
     d = str(tmp_path / "net")
-    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "t", "--routing", routing],
-                   check=True, stdout=subprocess.DEVNULL)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "t", "--routing", routing]
+    for k, v in params.items():
+        cmd += ["--param", f"{k}={v}"]
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     return os.path.join(d, "t.conf")
 
 
@@ -328,3 +339,15 @@ def test_random_configurations_match_reference_sources(ref_oracle):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "20 cases" in r.stdout and "0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("name,radix,conns,k,opts", TOPO_K_CASES, ids=[c[0] for c in TOPO_K_CASES])
+def test_restatement_matches_reference_sources_k_picks(tmp_path, ref_oracle, name, radix, conns, k, opts):
+    conf = make_topology(tmp_path, radix, conns, "prog-adaptive", global_k_picks=k)
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
+    ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
+    res = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert ev == res.events
+    r, o = oracle_util.read_dir(rdir), oracle_util.read_dir(odir)
+    for f in oracle_util.REF_FILES:
+        assert r.get(f) == o.get(f), f

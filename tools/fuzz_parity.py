@@ -18,7 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tests import oracle_util  # noqa: E402
 
-SHAPES = [(7, 1), (11, 1), (11, 2), (15, 1), (15, 2), (19, 2), (23, 4)]
+# (radix, links between groups); (11, 9) / (15, 16) / (15, 8) / (11, 6) have routers with several links to one group
+SHAPES = [(7, 1), (11, 1), (11, 2), (15, 1), (15, 2), (19, 2), (23, 4), (11, 9), (15, 16), (15, 8), (11, 6)]
 
 
 def make_case(rng):
@@ -36,6 +37,16 @@ def make_case(rng):
         params["router_delay"] = rng.choice(["0", "50", "300"])
     if rng.random() < 0.3:
         params["credit_delay"] = rng.choice(["10", "50", "100"])
+    if rng.random() < 0.2:
+        params[rng.choice(["cn_delay", "local_delay", "global_delay"])] = rng.choice(["5", "30", "250"])
+    if rng.random() < 0.15:
+        params[rng.choice(["cn_credit_delay", "local_credit_delay", "global_credit_delay"])] = rng.choice(["2", "20"])
+    if rng.random() < 0.15:
+        params["nic_seq_delay"] = rng.choice(["0", "25", "400"])
+    if rng.random() < 0.1:
+        params["credit_size"] = rng.choice(["4", "16", "64"])
+    if rng.random() < 0.1:
+        params["global_k_picks"] = rng.choice(["1", "2"])  # k > links to one group hangs the reference (dally:1822-1839)
     if routing == "prog-adaptive":
         if rng.random() < 0.5:
             params["adaptive_threshold"] = str(rng.choice([0, chunk, 4 * chunk]))
