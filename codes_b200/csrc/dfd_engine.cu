@@ -1167,9 +1167,11 @@ __device__ __forceinline__ void select_intermediate_group(const DfdParams& P, co
     } else {
         // re-pick among the groups this router links to directly (set<int>: ascending, unique)
         const int* gg = A.gs_group + (size_t)R.r * P.h;
+        // (a router may have fewer links than global ports: unused slots of the by-gid list hold INT_MAX, at the end)
         int nvalid = 0, prev = -1;
         for (int i = 0; i < P.h; i++) {
             int g = gg[i];
+            if (g == 0x7FFFFFFF) break;
             if (g != prev && g != fg && g != og) nvalid++;
             prev = g;
         }
@@ -1177,6 +1179,7 @@ __device__ __forceinline__ void select_intermediate_group(const DfdParams& P, co
         prev = -1;
         for (int i = 0; i < P.h; i++) {
             int g = gg[i];
+            if (g == 0x7FFFFFFF) break;
             if (g != prev && g != fg && g != og) {
                 if (sel == 0) {
                     m.intm_grp_id = (int16_t)g;

@@ -224,7 +224,7 @@ def test_large_network_matches_golden(tmp_path, gold_name, radix, conns, n, msgs
     assert all(r["avg_hops"] <= max_hops for r in cn if r["avg_hops"] == r["avg_hops"])  # NaN: a terminal that received nothing
 
 
-from tests.test_oracle_cpu import TOPO_CASES, TOPO_K_CASES, make_topology
+from tests.test_oracle_cpu import SWITCH_CONN_CASES, TOPO_CASES, TOPO_K_CASES, make_topology
 
 
 @pytest.mark.parametrize("name,radix,conns,routing,opts", TOPO_CASES, ids=[c[0] for c in TOPO_CASES])
@@ -294,3 +294,11 @@ def test_k_picks_larger_than_the_link_count_is_an_error_not_a_hang(tmp_path):
     conf = make_topology(tmp_path, 11, 9, "prog-adaptive", global_k_picks=3)
     with pytest.raises(codes_b200.EngineError, match="dead end"):
         codes_b200.run_synthetic(conf, num_messages=8, arrival_time=300.0)
+
+
+@pytest.mark.parametrize("name,radix,conns,routing,opts", SWITCH_CONN_CASES, ids=[c[0] for c in SWITCH_CONN_CASES])
+def test_engine_matches_oracle_parallel_local_links(tmp_path, name, radix, conns, routing, opts):
+    """num_parallel_switch_conns=2: every local hop has two candidate ports (one more draw per hop)."""
+    conf = make_topology(tmp_path, radix, conns, routing, switch_conns=2)
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)

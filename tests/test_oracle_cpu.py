@@ -305,11 +305,12 @@ TOPO_K_CASES = [  # global_k_picks other than the default 2
 ]
 
 
-def make_topology(tmp_path, radix, conns, routing, **params):
+def make_topology(tmp_path, radix, conns, routing, switch_conns=1, **params):
     import subprocess
     import sys
     d = str(tmp_path / "net")
-    cmd = [sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "t", "--routing", routing]
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "t", "--routing", routing,
+           "--switch-conns", str(switch_conns)]
     for k, v in params.items():
         cmd += ["--param", f"{k}={v}"]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
@@ -344,6 +345,25 @@ def test_random_configurations_match_reference_sources(ref_oracle):
 @pytest.mark.parametrize("name,radix,conns,k,opts", TOPO_K_CASES, ids=[c[0] for c in TOPO_K_CASES])
 def test_restatement_matches_reference_sources_k_picks(tmp_path, ref_oracle, name, radix, conns, k, opts):
     conf = make_topology(tmp_path, radix, conns, "prog-adaptive", global_k_picks=k)
+    rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
+    ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
+    res = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert ev == res.events
+    r, o = oracle_util.read_dir(rdir), oracle_util.read_dir(odir)
+    for f in oracle_util.REF_FILES:
+        assert r.get(f) == o.get(f), f
+
+
+SWITCH_CONN_CASES = [  # two parallel local links between every pair of routers of a group (num_parallel_switch_conns=2)
+    ("r7c1-minimal-2-local-links", 7, 1, "minimal", dict(num_messages=8, arrival_time=300.0)),
+    ("r11c1-par-2-local-links", 11, 1, "prog-adaptive", dict(num_messages=8, traffic=3)),
+    ("r11c2-nonminimal-2-local-links", 11, 2, "nonminimal", dict(num_messages=6)),
+]
+
+
+@pytest.mark.parametrize("name,radix,conns,routing,opts", SWITCH_CONN_CASES, ids=[c[0] for c in SWITCH_CONN_CASES])
+def test_restatement_matches_reference_sources_parallel_local_links(tmp_path, ref_oracle, name, radix, conns, routing, opts):
+    conf = make_topology(tmp_path, radix, conns, routing, switch_conns=2)
     rdir, odir = str(tmp_path / "ref"), str(tmp_path / "or")
     ev, _, out = oracle_util.run_ref(conf, rdir, **opts)
     res = oracle_util.run(conf, lp_io_dir=odir, **opts)

@@ -62,15 +62,18 @@ def make_case(rng):
         opts["warm_up_time"] = rng.choice([500.0, 3000.0])
     if rng.random() < 0.15:
         opts["end_time"] = rng.choice([4000.0, 20000.0])
+    if rng.random() < 0.15:
+        params["_switch_conns"] = 2
     return radix, conns, routing, params, opts
 
 
 def write_conf(tmp, radix, conns, routing, params):
     net = os.path.join(tmp, "net")
     cmd = [sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), net, "--name", "t", "--routing", routing,
-           "--chunk-size", str(params["chunk_size"]), "--packet-size", str(params["packet_size"])]
+           "--chunk-size", str(params["chunk_size"]), "--packet-size", str(params["packet_size"]),
+           "--switch-conns", str(params.get("_switch_conns", 1))]
     for k, v in params.items():
-        if k not in ("chunk_size", "packet_size"):
+        if k not in ("chunk_size", "packet_size", "_switch_conns"):
             cmd += ["--param", f"{k}={v}"]
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     return os.path.join(net, "t.conf")

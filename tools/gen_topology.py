@@ -28,8 +28,9 @@ def dims(radix, conns):
     return a, p, h, g
 
 
-def intra_records(a):
-    return [(s, d, 0) for s in range(a) for d in range(a) if s != d]
+def intra_records(a, switch_conns=1):
+    # switch_conns parallel local links between every ordered pair of routers (PARAMS num_parallel_switch_conns)
+    return [(s, d, 0) for s in range(a) for d in range(a) if s != d for _ in range(switch_conns)]
 
 
 def inter_records(a, h, g, conns):
@@ -84,19 +85,21 @@ PARAMS
 
 
 def write_config(out_dir, name, radix, conns, routing="minimal", packet_size=4096, chunk_size=4096,
-                 local_vc=16384, global_vc=16384, cn_vc=32768, bw="2.0", extra=None):
+                 local_vc=16384, global_vc=16384, cn_vc=32768, bw="2.0", extra=None, switch_conns=1):
     a, p, h, g = dims(radix, conns)
     os.makedirs(out_dir, exist_ok=True)
     intra = os.path.join(out_dir, f"{name}-intra")
     inter = os.path.join(out_dir, f"{name}-inter")
     with open(intra, "wb") as f:
-        for r in intra_records(a):
+        for r in intra_records(a, switch_conns):
             f.write(struct.pack("3i", *r))
     with open(inter, "wb") as f:
         for r in inter_records(a, h, g, conns):
             f.write(struct.pack("2i", *r))
     extra_lines = ""
     ex = dict(extra or {})
+    if switch_conns != 1:
+        ex["num_parallel_switch_conns"] = str(switch_conns)
     if routing == "prog-adaptive":
         ex.setdefault("adaptive_threshold", "16384")
         ex.setdefault("route_scoring_metric", "delta")
@@ -132,13 +135,14 @@ def main():
     ap.add_argument("--routing", default="minimal")
     ap.add_argument("--packet-size", type=int, default=4096)
     ap.add_argument("--chunk-size", type=int, default=4096)
+    ap.add_argument("--switch-conns", type=int, default=1, help="parallel local links between each pair of routers of a group")
     ap.add_argument("--param", action="append", default=[], help="extra PARAMS key=value")
     args = ap.parse_args()
     a, p, h, g = dims(args.radix, args.conns)
     name = args.name or f"dfdally-{a * g * p}"
     extra = dict(kv.split("=", 1) for kv in args.param)
     conf, d = write_config(args.out_dir, name, args.radix, args.conns, routing=args.routing,
-                           packet_size=args.packet_size, chunk_size=args.chunk_size, extra=extra)
+                           packet_size=args.packet_size, chunk_size=args.chunk_size, extra=extra, switch_conns=args.switch_conns)
     print(conf, d)
 
 
