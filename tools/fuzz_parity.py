@@ -64,6 +64,12 @@ def make_case(rng):
         opts["end_time"] = rng.choice([4000.0, 20000.0])
     if rng.random() < 0.15:
         params["_switch_conns"] = 2
+    if opts["traffic"] == 2 and rng.random() < 0.6:
+        # RAND_PERM produces self-sends: they take the same-node shortcut of model-net.c:305-309 as long as the message is
+        # below node_eager_limit and codes_noop_bypass is off; otherwise the reference asserts (dally:5428)
+        params["node_eager_limit"] = str(opts["payload_sz"] + rng.choice([1, 100, 100000]))
+        if rng.random() < 0.5:
+            params["codes_noop_bypass"] = "0"
     return radix, conns, routing, params, opts
 
 
