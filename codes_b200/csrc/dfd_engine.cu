@@ -237,11 +237,11 @@ __device__ __forceinline__ void push_chunk_remote(Ctx& c, unsigned me, unsigned 
     size_t lane = ((size_t)c.nxt * P.NR + r) * P.h + kp;
     unsigned packed;
     unsigned idx = xlane_reserve(c, me * P.h + my_gport, false, &packed);
-    if (idx >= DFD_XLANE_CAP) {
+    if (idx >= (unsigned)P.xlane_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
     }
-    int4* dst = (int4*)on_rank(X, &A.xc[lane * DFD_XLANE_CAP + idx], owner);
+    int4* dst = (int4*)on_rank(X, &A.xc[lane * P.xlane_cap + idx], owner);
     const int4* src = (const int4*)&rec;
 #pragma unroll
     for (int i = 0; i < 6; i++) __stcg(dst + i, src[i]);
@@ -258,7 +258,7 @@ __device__ __forceinline__ void push_credit_remote(Ctx& c, unsigned me, unsigned
     size_t lane = ((size_t)c.nxt * P.NR + r) * P.h + kp;
     unsigned packed;
     unsigned idx = xlane_reserve(c, me * P.h + my_gport, true, &packed);
-    if (idx >= DFD_XLANE_CAP) {
+    if (idx >= (unsigned)P.xlane_cap) {
         set_error(A, DFD_ERR_INBOX_OVERFLOW, r);
         return;
     }
@@ -271,7 +271,7 @@ __device__ __forceinline__ void push_credit_remote(Ctx& c, unsigned me, unsigned
     rec.pad0 = 0;
     rec.pad1 = 0;
     rec.pad2 = 0;
-    int4* dst = (int4*)on_rank(X, &A.xk[lane * DFD_XLANE_CAP + idx], owner);
+    int4* dst = (int4*)on_rank(X, &A.xk[lane * P.xlane_cap + idx], owner);
     __stcg(dst, ((const int4*)&rec)[0]);
     __stcg(dst + 1, ((const int4*)&rec)[1]);
     xlane_publish(c, lane, r, kp, packed, owner);
@@ -1666,8 +1666,8 @@ __device__ void router_process(Ctx& c, unsigned r, unsigned ntail_c, unsigned nt
                 size_t lane = ((size_t)c.cur * P.NR + r) * P.h + kp;
                 unsigned cnt = __ldcg(&A.xcnt[lane]);
                 A.xcnt[lane] = 0;
-                if (cnt & 0xFFFFu) drain_chunks(c, R, &A.xc[lane * DFD_XLANE_CAP], cnt & 0xFFFFu);
-                if (cnt >> 16) drain_credits(c, R, &A.xk[lane * DFD_XLANE_CAP], cnt >> 16);
+                if (cnt & 0xFFFFu) drain_chunks(c, R, &A.xc[lane * P.xlane_cap], cnt & 0xFFFFu);
+                if (cnt >> 16) drain_credits(c, R, &A.xk[lane * P.xlane_cap], cnt >> 16);
             } while (xm);
         }
     }
@@ -2177,9 +2177,9 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
             return 1;
         }
         const size_t lanes = 2 * NR * (size_t)P.h;
-        off = align256(off + lanes * DFD_XLANE_CAP * sizeof(ChunkRec));
+        off = align256(off + lanes * (size_t)P.xlane_cap * sizeof(ChunkRec));
         o_xk = off;
-        off = align256(off + lanes * DFD_XLANE_CAP * sizeof(CreditRec));
+        off = align256(off + lanes * (size_t)P.xlane_cap * sizeof(CreditRec));
         o_xn = off;
         off = align256(off + lanes * sizeof(unsigned));
         o_xm = off;

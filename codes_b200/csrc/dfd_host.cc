@@ -968,6 +968,9 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->rcin_cap = (int)in_chunks;
     P->rkin_cap = (int)out_chunks;
     P->rpool_cap = (int)(in_chunks + out_chunks);
+    // a sender never has more than VCs * vc_size / chunk_size uncredited chunks on one global link, and a link returns at
+    // most that many credits: no window can carry more records over it
+    P->xlane_cap = next_pow2(std::max(8, DFD_NUM_VCS * glb_chunks));
     P->rheap_cap = (int)(in_chunks + out_chunks + p.radix + 1);
     {   // timing wheel: must span the largest delay between a router event's creation and its timestamp
         double maxbw_inj = std::max(h_bytes_to_ns(p.chunk_size, p.cn_bandwidth), std::max(h_bytes_to_ns(p.chunk_size, p.local_bandwidth), h_bytes_to_ns(p.chunk_size, p.global_bandwidth)));
@@ -1044,7 +1047,7 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
         reuse = Q.NT == P.NT && Q.NR == P.NR && Q.radix == P.radix && Q.a == P.a && Q.p == P.p && Q.G == P.G && Q.h == P.h &&
                 Q.ncin_cap == P.ncin_cap && Q.nkin_cap == P.nkin_cap && Q.nsq_cap == P.nsq_cap && Q.ntq_cap == P.ntq_cap &&
                 Q.nev_cap == P.nev_cap && Q.nreasm_cap == P.nreasm_cap && Q.rcin_cap == P.rcin_cap && Q.rkin_cap == P.rkin_cap &&
-                Q.rpool_cap == P.rpool_cap && Q.rheap_cap == P.rheap_cap && Q.wheel_nb == P.wheel_nb;
+                Q.rpool_cap == P.rpool_cap && Q.xlane_cap == P.xlane_cap && Q.rheap_cap == P.rheap_cap && Q.wheel_nb == P.wheel_nb;
     }
     if (reuse) {
         e->dev.P = P;

@@ -251,6 +251,7 @@ struct DfdParams {
     int ncin_cap, nkin_cap, nsq_cap, ntq_cap, nev_cap;
     int nreasm_cap;  // per-terminal reassembly table entries (0: every message is one chunk)
     int rcin_cap, rkin_cap, rpool_cap, rheap_cap;
+    int xlane_cap;   // records one cross-GPU global link can carry per window and direction (chunks and credits each)
     int wheel_nb;        // buckets of a router's timing wheel (power of two, >= max event delay / window + slack)
     double inv_window;   // 1 / (wheel bucket width)
 };
@@ -286,8 +287,8 @@ struct DfdArrays {
     unsigned* wheel;             // [NR][wheel_nb]    bucket heads
     unsigned long long* wbits;   // [NR][wheel_nb/64] non-empty-bucket bitmap
     // cross-GPU global links (world > 1): one single-writer lane per (router, global port) and window parity
-    ChunkRec* xc;                // [2][NR][h][DFD_XLANE_CAP]
-    CreditRec* xk;               // [2][NR][h][DFD_XLANE_CAP]
+    ChunkRec* xc;                // [2][NR][h][xlane_cap]
+    CreditRec* xk;               // [2][NR][h][xlane_cap]
     unsigned* xcnt;              // [2][NR][h]  chunks | credits << 16 written into the lane this window
     unsigned long long* xmask;   // [2][NR]     bit k: lane k holds records
     uint2* xsend;                // [NR][h]     sender side: {window stamp, packed counts} of the lane behind my port
@@ -315,7 +316,6 @@ struct DfdArrays {
 // (written straight into the owner's router inbox through a CUDA-IPC mapping of its exchange region) and the
 // svr->svr ACK statistics.  One window = local grid barrier, flag + minimum exchange over NVLink, local barrier.
 #define DFD_MAX_RANKS 8
-enum { DFD_XLANE_CAP = 8 };  // records one link can carry per window and direction (chunks and credits each)
 // lives at the start of every rank's exchange region.  mins[w%3][k]: rank k's earliest pending timestamp for
 // window w, written by rank k when it closes window w-1; DFD_SYNC_EMPTY until then, DFD_SYNC_FAILED if rank k
 // raised a device error.

@@ -3,6 +3,7 @@
 
   python tools/fuzz_parity.py ref  [--cases N] [--seed S]   restatement oracle vs oracle/_ref (reference sources)  -- CPU
   python tools/fuzz_parity.py gpu  [--cases N] [--seed S]   CUDA engine vs restatement oracle                      -- GPU box
+  python -m torch.distributed.run --nproc-per-node G tools/fuzz_parity.py mgpu ...   group-sharded engine over G GPUs vs oracle
 
 Every case compares all lp-io files (and, on the GPU, the hex-float raw statistics) byte for byte.  A case whose
 configuration the reference itself rejects is skipped when both sides reject it."""
@@ -87,14 +88,21 @@ def write_conf(tmp, radix, conns, routing, params):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["ref", "gpu"])
+    ap.add_argument("mode", choices=["ref", "gpu", "mgpu"])
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
     args = ap.parse_args()
     rng = random.Random(args.seed)
     oracle_util.load()
-    if args.mode == "gpu":
+    if args.mode in ("gpu", "mgpu"):
         import codes_b200
+    dist, rank = None, 0
+    if args.mode == "mgpu":  # every rank generates the same cases from the same seed; rank 0 checks
+        import torch
+        import torch.distributed as dist
+        rank = int(os.environ["RANK"])
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+        dist.init_process_group("cpu:gloo,cuda:nccl")
     bad = skipped = 0
     for i in range(args.cases):
         radix, conns, routing, params, opts = make_case(rng)
@@ -107,6 +115,24 @@ def main():
                 oerr = None
             except oracle_util.OracleError as ex:
                 oerr = str(ex)
+            if args.mode == "mgpu":
+                groups = int(open(conf).read().split('num_groups="')[1].split('"')[0])
+                if groups < dist.get_world_size():
+                    skipped += 1
+                    continue
+                flag = [oerr]
+                dist.broadcast_object_list(flag, src=0)  # the oracle's verdict of rank 0 decides for everybody
+                if flag[0]:
+                    skipped += 1
+                    continue
+                s = codes_b200.run_sharded(conf, dist, lp_io_dir=os.path.join(tmp, "g") if rank == 0 else None, **opts)
+                if rank == 0:
+                    g = oracle_util.read_dir(os.path.join(tmp, "g"))
+                    diffs = [k for k in o if g.get(k) != o[k]]
+                    if s.events != res.events or diffs:
+                        print("MISMATCH", tag, "events", s.events, res.events, diffs, flush=True)
+                        bad += 1
+                continue
             if args.mode == "ref":
                 try:
                     ev, _, _ = oracle_util.run_ref(conf, os.path.join(tmp, "r"), **opts)
@@ -143,6 +169,14 @@ def main():
                 if s.events != res.events or diffs:
                     print("MISMATCH", tag, "events", s.events, res.events, diffs, flush=True)
                     bad += 1
+    if dist is not None:
+        dist.barrier()
+        world = dist.get_world_size()
+        dist.destroy_process_group()
+        if rank != 0:
+            sys.exit(0)
+        print(f"mgpu ({world} GPUs): {args.cases} cases, {skipped} skipped (fewer groups than GPUs / rejected), {bad} mismatches")
+        sys.exit(1 if bad else 0)
     print(f"{args.mode}: {args.cases} cases, {skipped} rejected by both sides, {bad} mismatches")
     sys.exit(1 if bad else 0)
 
