@@ -278,7 +278,7 @@ int read_params(dfd_engine* e) {
     if (g.getd("cn_bandwidth", &p.cn_bandwidth)) p.cn_bandwidth = 5.25;
     if (g.getd("router_delay", &p.router_delay)) p.router_delay = 100;
     int v = 1;
-    if (!g.geti("num_qos_levels", &v) && v != 1) return fail(e, "num_qos_levels > 1 is not supported by this engine (SURVEY 8f-1)");
+    if (!g.geti("num_qos_levels", &v) && v != 1) return fail(e, "\n priority needs to be specified with qos_levels>1 (the synthetic driver sends category \"test\": the reference aborts here too, dally:3248-3254)");
     if (g.geti("adaptive_threshold", &p.adaptive_threshold)) p.adaptive_threshold = 0;
     std::string rt = g.gets("routing");
     if (rt == "minimal")

@@ -98,7 +98,7 @@ def configure(conf, **opts):
     (dict(num_routers="5"), "Config error"),                                    # dally:4925-4931
     (dict(message_size="512"), "ROSS is configured for events of size"),       # model-net.c:294-300
     (dict(intra__group__connections="/nonexistent"), "intra-group file not found"),
-    (dict(num_qos_levels="2"), "num_qos_levels"),
+    (dict(num_qos_levels="2"), "priority needs to be specified with qos_levels>1"),  # the reference's own abort (dally:3254)
     (dict(modelnet_scheduler="round-robin"), "modelnet_scheduler"),
 ])
 def test_config_errors_match_reference_behaviour(engine_lib, tmp_path, changes, msg):
