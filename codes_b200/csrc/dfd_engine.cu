@@ -474,8 +474,19 @@ __device__ __forceinline__ void mn_sched_next(Ctx& c, unsigned n, NodeState* s, 
 __device__ void mn_new_msg(Ctx& c, unsigned n, NodeState* s, NodeEv* list, double now, const NodeEv& ev) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
-    if (ev.a == n) {  // lp->gid == dest_mn_lp: self-addressed message above the eager limit
-        set_error(A, DFD_ERR_SELF_SEND, n);
+    if (ev.a == n) {
+        // lp->gid == dest_mn_lp: a message to the sender's own terminal that did not take the no-op shortcut (size >=
+        // node_eager_limit, or codes_noop_bypass): the base LP copies it inside the node, model-net-lp.c:672-704 (one
+        // node-copy queue); remote event to the destination svr, then the self event to the sender, both from this LP
+        double exp_time = (s->node_copy_next_available_time > now) ? s->node_copy_next_available_time : now;
+        exp_time += (double)(unsigned long long)ev.b * P.codes_cn_delay;
+        exp_time -= now;
+        double delay = node_cll(P, s, s->rng_term2);
+        s->node_copy_next_available_time = now + exp_time;
+        exp_time += delay;
+        node_add_event(c, n, s, list, now + exp_time, s->term_gid, s->term_seq++, EV_REMOTE, n, 0, 0, ev.d);
+        exp_time += delay;
+        node_add_event(c, n, s, list, now + exp_time, s->term_gid, s->term_seq++, EV_LOCAL);
         return;
     }
     if (ev.type & NEV_FLAG_QREQ) {

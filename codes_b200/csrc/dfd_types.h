@@ -221,6 +221,8 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t local_sr, local_sg, remote_pk, minimal_count, nonmin_count, pad2;
     uint32_t svr_gid, term_gid;
     uint32_t mt_n, pt_n;  // live entries of the message / packet reassembly tables
+    double node_copy_next_available_time;  // model_net_base_state.node_copy_next_available_time[0] (model-net-lp.c:672-704)
+    double pad_d;
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)

@@ -710,6 +710,7 @@ struct TermState {
     // model_net_base_state model-net-lp.c:50-74
     uint64_t msg_id = 0;
     double next_available_time = 0;
+    double node_copy_next_available_time = 0;  // model_net_base_state.node_copy_next_available_time[0]
     int in_sched_send_loop = 0;
     std::deque<Req> sched_q;  // fcfs queue model-net-sched-impl.c:128-261
     // terminal_state dally:703-820
@@ -1029,7 +1030,31 @@ public:
     }
     void handle_new_msg(uint64_t gid, const Event& ev) {  // model-net-lp.c:643-802
         TermState& s = term[term_rel(gid)];
-        if (gid == ev.rq.dest_mn_lp) die("self-addressed network message above the eager limit is out of scope");
+        if (gid == ev.rq.dest_mn_lp) {
+            // message to the sender's own terminal that did not take the no-op shortcut (size >= node_eager_limit, or
+            // codes_noop_bypass): the base LP copies it inside the node, model-net-lp.c:672-704 (one node-copy queue)
+            const Req& r = ev.rq;
+            double exp_time = (s.node_copy_next_available_time > now) ? s.node_copy_next_available_time : now;
+            exp_time += r.msg_size * p.codes_cn_delay;
+            exp_time -= now;
+            double delay = codes_local_latency(gid);
+            s.node_copy_next_available_time = now + exp_time;
+            if (r.remote_event_size > 0) {
+                exp_time += delay;
+                Event& e = ev_new(r.final_dest_lp, exp_time, SVR_REMOTE);
+                e.m.ev_src = r.ev_src;
+                e.m.ev_start_time = r.ev_start_time;
+                ev_send();
+            }
+            if (r.self_event_size > 0) {
+                exp_time += delay;
+                Event& e = ev_new(r.src_lp, exp_time, SVR_LOCAL);
+                e.m.ev_src = r.ev_src;
+                e.m.ev_start_time = r.ev_start_time;
+                ev_send();
+            }
+            return;
+        }
         if (ev.qreq) {
             double exp_time = (s.next_available_time > now) ? s.next_available_time : now;
             exp_time += p.nic_seq_delay + codes_local_latency(gid);

@@ -94,6 +94,9 @@ VARIANTS = [
     ("72-multichunk", CONF72, dict(chunk_size="1024"), dict(num_messages=10)),                       # packets of 2 chunks
     ("72-multipacket", CONF72, dict(packet_size="1024", chunk_size="1024"), dict(num_messages=10)),  # messages of 2 packets
     ("72-multi-both", CONF72, dict(packet_size="2048", chunk_size="512"), dict(num_messages=6, payload_sz=5000)),
+    # RAND_PERM self-sends that do not take the no-op shortcut: copied inside the node by the base LP (model-net-lp.c:672-704)
+    ("72-self-copy-bypass", CONF72, dict(codes_noop_bypass="1"), dict(num_messages=12, traffic=2)),
+    ("72-self-copy-eager-limit", CONF72, dict(node_eager_limit="100"), dict(num_messages=12, traffic=2, payload_sz=4096, arrival_time=300.0)),
     ("72-multi-par", CONF72, dict(packet_size="2048", chunk_size="512", routing="prog-adaptive"), dict(num_messages=8, payload_sz=6000, traffic=3)),
     ("72-big-payload", CONF72, dict(), dict(num_messages=5, payload_sz=20000)),                        # 5 packets per message
     ("1056-nonminimal", CONF1056, dict(routing="nonminimal"), dict(num_messages=4)),

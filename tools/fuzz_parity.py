@@ -66,11 +66,11 @@ def make_case(rng):
     if rng.random() < 0.15:
         params["_switch_conns"] = 2
     if opts["traffic"] == 2 and rng.random() < 0.6:
-        # RAND_PERM produces self-sends: they take the same-node shortcut of model-net.c:305-309 as long as the message is
-        # below node_eager_limit and codes_noop_bypass is off; otherwise the reference asserts (dally:5428)
-        params["node_eager_limit"] = str(opts["payload_sz"] + rng.choice([1, 100, 100000]))
+        # RAND_PERM produces self-sends: below node_eager_limit they take the no-op shortcut of model-net.c:305-309,
+        # otherwise (or with codes_noop_bypass) the base LP copies them inside the node (model-net-lp.c:672-704)
+        params["node_eager_limit"] = rng.choice(["0", "100", "5000", "100000"])
         if rng.random() < 0.5:
-            params["codes_noop_bypass"] = "0"
+            params["codes_noop_bypass"] = rng.choice(["0", "1"])
     return radix, conns, routing, params, opts
 
 
