@@ -48,8 +48,8 @@ class Summary(ctypes.Structure):
                 ("device_bytes", ctypes.c_ulonglong),
                 ("grid_blocks", ctypes.c_int), ("block_threads", ctypes.c_int), ("num_sms", ctypes.c_int),
                 ("num_terminals", ctypes.c_int), ("num_routers", ctypes.c_int), ("radix", ctypes.c_int),
-                ("cyc_scan", ctypes.c_double), ("cyc_process", ctypes.c_double), ("cyc_barrier", ctypes.c_double),
-                ("cyc_process_max_block", ctypes.c_double), ("cyc_process_longest", ctypes.c_double)]
+                ("cyc_busy", ctypes.c_double), ("cyc_idle", ctypes.c_double), ("cyc_busy_max_warp", ctypes.c_double),
+                ("activations", ctypes.c_ulonglong), ("passes", ctypes.c_ulonglong)]
 
     def as_dict(self):
         d = {}
@@ -109,15 +109,9 @@ ABI = [
 ]
 
 
-def load_library():
-    """Load libdfdally_b200.so (built by __graft_entry__.build() / `make -C codes_b200/csrc`)."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise EngineError(f"{LIB_PATH} is missing: build it with `make -C codes_b200/csrc` "
-                          "(there is no CPU fallback for the dragonfly-dally engine)")
-    lib = ctypes.CDLL(LIB_PATH)
+def bind_library(path):
+    """ctypes-bind one build of the C-ABI (every symbol of include/dfdally_b200.h) and check the struct mirrors."""
+    lib = ctypes.CDLL(path)
     for name, res, args in ABI:
         fn = getattr(lib, name)
         fn.restype = res
@@ -126,10 +120,21 @@ def load_library():
     a, b = ctypes.c_int(0), ctypes.c_int(0)
     lib.dfd_abi_sizes(ctypes.byref(a), ctypes.byref(b))
     if (a.value, b.value) != (ctypes.sizeof(Summary), ctypes.sizeof(SyntheticOpts)):
-        raise EngineError(f"{LIB_PATH}: dfd_summary / dfd_synthetic_opts are {a.value} / {b.value} bytes in the library but "
+        raise EngineError(f"{path}: dfd_summary / dfd_synthetic_opts are {a.value} / {b.value} bytes in the library but "
                           f"{ctypes.sizeof(Summary)} / {ctypes.sizeof(SyntheticOpts)} in this binding: rebuild one of them")
-    _lib = lib
     return lib
+
+
+def load_library():
+    """Load libdfdally_b200.so (built by __graft_entry__.build() / `make -C codes_b200/csrc`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(f"{LIB_PATH} is missing: build it with `make -C codes_b200/csrc` "
+                          "(there is no CPU fallback for the dragonfly-dally engine)")
+    _lib = bind_library(LIB_PATH)
+    return _lib
 
 
 def bytes_to_ns(nbytes, gib_per_s):
@@ -158,10 +163,11 @@ def make_opts(traffic=UNIFORM, num_messages=20, payload_sz=2048, rperm_threshold
 class Engine:
     """One simulation context (the reference keeps this in file-scope globals)."""
 
-    def __init__(self):
-        self._lib = load_library()
+    def __init__(self, lib=None):
+        self._lib = lib or load_library()
         self._h = _P()
-        self._lib.dfd_engine_create(ctypes.byref(self._h))
+        if self._lib.dfd_engine_create(ctypes.byref(self._h)) != 0 or not self._h:
+            raise EngineError("dfd_engine_create failed")
 
     def close(self):
         if self._h:
@@ -289,9 +295,9 @@ class Engine:
         return s
 
 
-def run_synthetic(conf_path, lp_io_dir=None, **opts):
+def run_synthetic(conf_path, lp_io_dir=None, lib=None, **opts):
     """The whole main() of model-net-synthetic-dragonfly-all on the GPU; returns a Summary."""
-    lib = load_library()
+    lib = lib or load_library()
     o = make_opts(**opts)
     s = Summary()
     err = ctypes.create_string_buffer(1024)

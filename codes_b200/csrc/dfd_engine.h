@@ -8,22 +8,17 @@
 
 #include "dfd_types.h"
 
-struct DfdSeedConsts {  // CLCG4 constants: moduli, default seed, a^(2^(31+41)) mod m (stream jump)
-    unsigned long long m[4], seed0[4], avw[4];
-};
-
 struct DfdHostTopo {  // flattened connection tables (see DfdArrays)
-    std::vector<int> loc_off, loc_port, loc_dest, gs_port, gs_group, gdest, routed_off, routed_lid;
+    std::vector<int> loc_off, loc_port, loc_dest, lout_lane, lin_src, gs_port, gs_group, gdest, gout_lane, gin_src, gin_port, routed_off, routed_lid;
 };
 
-struct DfdHostResults {
+struct DfdHostResults {  // indexed by GLOBAL node / router id; a rank fills its own slice
     std::vector<NodeState> node;
     std::vector<RouterHdr> rh;
     std::vector<PortState> port;
     std::vector<unsigned> ack_count;
     std::vector<unsigned long long> ack_first, ack_last;
     unsigned long long counters[64];
-    std::vector<unsigned long long> winmax;
     size_t d2h_bytes = 0;
 };
 
@@ -34,10 +29,13 @@ struct DfdDevice {
     DfdPeers X;
     char* xregion = nullptr;
     size_t xregion_bytes = 0;
-    size_t x_zero_off = 0, x_zero_bytes = 0;  // lane counts + masks inside the exchange region (sharded runs)
+    size_t x_ack_off = 0;  // start of the ACK arrays inside the exchange region
+    int ntl = 0, nrl = 0;        // nodes / routers owned by this rank
+    int ntmax = 0, nrmax = 0;    // largest partition of any rank (exchange-region strides)
     std::vector<void*> ipc_opened;
     std::vector<void*> allocs;
     size_t bytes_allocated = 0, topo_bytes = 0;
+    std::vector<size_t> topo_sizes;  // element counts of the uploaded tables (reuse check)
     int num_sms = 0, grid = 0, block = 0, blocks_per_sm = 0;
     size_t smem = 0;
     const void* kernel = nullptr;  // dfd_run_kernel instantiation in use
@@ -50,7 +48,6 @@ int dfd_device_ipc_export(DfdDevice* dev, void* handle64);
 int dfd_device_ipc_import(DfdDevice* dev, const void* handles, int world);
 int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st);
 int dfd_device_reset(DfdDevice* dev, cudaStream_t st);
-int dfd_device_run(DfdDevice* dev, cudaStream_t st, unsigned long long max_windows);
+int dfd_device_run(DfdDevice* dev, cudaStream_t st);
 int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st);
-int dfd_device_read_counters(DfdDevice* dev, unsigned long long* counters, cudaStream_t st);
 void dfd_device_destroy(DfdDevice* dev);

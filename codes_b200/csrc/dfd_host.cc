@@ -452,6 +452,41 @@ int build_topology(dfd_engine* e) {
         }
         e->glinks_by_gid[r] = v;
     }
+    // --- lanes: every directed link feeds one in-lane of its destination.  Local in-lanes of router-local id d are
+    // numbered in (source lid, source port) order, global in-lanes of router d in (source router, source port) order;
+    // a lane has the same index range as the ports of its kind, so capacities follow from the index alone.
+    T.lout_lane.assign((size_t)a * std::max(1, p.intra_grp_radix), -1);
+    T.lin_src.assign((size_t)a * std::max(1, p.intra_grp_radix), -1);
+    {
+        std::vector<int> nin(a, 0);
+        for (int sl = 0; sl < a; sl++)
+            for (int port = 0; port < p.intra_grp_radix; port++) {
+                int d = T.loc_dest[(size_t)sl * p.intra_grp_radix + port];
+                if (d < 0) continue;
+                if (nin[d] >= p.intra_grp_radix)
+                    return fail(e, "local router %d is the destination of more than %d local links (> intra-group radix)", d, p.intra_grp_radix);
+                int lane = nin[d]++;
+                T.lout_lane[(size_t)sl * p.intra_grp_radix + port] = lane;
+                T.lin_src[(size_t)d * p.intra_grp_radix + lane] = (sl << 16) | port;
+            }
+    }
+    T.gout_lane.assign((size_t)NR * std::max(1, h), -1);
+    T.gin_src.assign((size_t)NR * std::max(1, h), -1);
+    T.gin_port.assign((size_t)NR * std::max(1, h), -1);
+    {
+        std::vector<int> nin(NR, 0);
+        for (int r = 0; r < NR; r++)
+            for (int i = 0; i < h; i++) {
+                int d = T.gdest[(size_t)r * h + i];
+                if (d < 0) continue;
+                if (nin[d] >= h)
+                    return fail(e, "router %d is the destination of more than %d global links (> num_global_channels): asymmetric link files are not supported", d, h);
+                int k = nin[d]++;
+                T.gout_lane[(size_t)r * h + i] = p.intra_grp_radix + k;
+                T.gin_src[(size_t)d * h + k] = r;
+                T.gin_port[(size_t)d * h + k] = p.intra_grp_radix + i;
+            }
+    }
     return 0;
 }
 
@@ -667,10 +702,10 @@ const char* device_error_name(unsigned long long code) {
     case DFD_ERR_WRONG_TERMINAL: return "Packet arrived at wrong terminal";
     case DFD_ERR_BAD_VC: return "Output channel greater than available VCs";
     case DFD_ERR_SELF_SEND: return "self-addressed network message above the eager limit";
-    case DFD_ERR_LATE_EVENT: return "event scheduled inside the current window";
-    case DFD_ERR_PEER_TIMEOUT: return "a peer GPU did not reach the window barrier";
+    case DFD_ERR_LATE_EVENT: return "causality violation: an LP received an event older than one it had already executed";
+    case DFD_ERR_PEER_TIMEOUT: return "a peer GPU stopped responding";
+    case DFD_ERR_STALL: return "no event became safe for the watchdog period although events are pending (info = pending events)";
     case DFD_ERR_PEER_ERROR: return "a peer GPU reported an error";
-    case DFD_ERR_WHEEL_RANGE: return "event delay outside the range of the router timing wheel";
     case DFD_ERR_REASM_OVERFLOW: return "too many messages being reassembled at one terminal (raise DFD_REASM_CAP)";
     }
     return "unknown";
@@ -920,16 +955,16 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->magic_p = p.num_cn > 1 ? (~0ULL) / (unsigned long long)p.num_cn + 1 : 0;
     P->magic_a = p.num_routers > 1 ? (~0ULL) / (unsigned long long)p.num_routers + 1 : 0;
     if (p.num_groups > 32767 || p.total_routers > (1 << 30)) return fail(e, "topology too large for the packed chunk record");
-    // lookahead window: the smallest delay of any event that crosses LPs (every chunk hop is at least
-    // its link delay; every credit exactly its credit delay)
+    // smallest delay of any event that crosses LPs (every chunk hop is at least its link delay; every credit exactly
+    // its credit delay): the asynchronous scheduler needs it strictly positive to make progress
     double L = p.cn_delay;
     L = std::min(L, p.local_delay);
     L = std::min(L, p.global_delay);
     L = std::min(L, p.cn_credit_delay);
     L = std::min(L, p.local_credit_delay);
     L = std::min(L, p.global_credit_delay);
-    if (!(L > 0)) return fail(e, "this engine needs strictly positive link and credit delays (lookahead window would be %g ns)", L);
-    P->window = L;
+    if (!(L > 0)) return fail(e, "this engine needs strictly positive link and credit delays (smallest is %g ns)", L);
+    P->min_delay = L;
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
     P->traffic = o.traffic;
     P->num_msgs = o.num_messages;
@@ -948,8 +983,8 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     // capacities: every bound below follows from the credit protocol (a sender never has more than
     // vc_size/chunk_size uncredited chunks per VC outstanding)
     int cn_chunks = p.cn_vc_size / p.chunk_size, loc_chunks = p.local_vc_size / p.chunk_size, glb_chunks = p.global_vc_size / p.chunk_size;
-    P->ncin_cap = next_pow2(DFD_NUM_VCS * cn_chunks + 1);
-    P->nkin_cap = next_pow2(cn_chunks + 1);
+    P->ncin_cap = next_pow2(DFD_NUM_VCS * cn_chunks);
+    P->nkin_cap = next_pow2(cn_chunks);
     P->nsq_cap = next_pow2(std::max(2, o.num_messages + 1));
     int chunks_per_packet = (int)((std::min<unsigned long long>(p.mn_packet_size, (unsigned long long)o.payload_sz) + p.chunk_size - 1) / p.chunk_size);
     if (chunks_per_packet < 1) chunks_per_packet = 1;
@@ -959,33 +994,40 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     bool multi = (unsigned long long)o.payload_sz > p.mn_packet_size || o.payload_sz > p.chunk_size;
     P->nreasm_cap = multi ? 256 : 0;
     if (const char* ev = getenv("DFD_REASM_CAP")) if (multi) P->nreasm_cap = std::max(4, std::min(4999, atoi(ev)));
+    // self events of a node: KICKOFF, the first-stage NEW_MSG, LOCAL / REMOTE completions, SCHED_NEXT, T_GENERATE, T_SEND.
+    // The second-stage NEW_MSG events, whose number grows with the burst length, live in their own FIFO (mq, nsq_cap).
     P->nev_cap = 24;
-    // in-degree per router type equals out-degree for the link files we accept (checked below)
+    if (const char* ev = getenv("DFD_NEV_CAP")) P->nev_cap = std::max(8, std::min(4096, atoi(ev)));
+    // lanes: one link carries at most VCs * vc_size / chunk_size uncredited chunks, and returns at most that many credits
+    P->ext = p.intra_grp_radix + p.global_radix;
+    P->cap_l = next_pow2(DFD_NUM_VCS * loc_chunks);
+    P->cap_g = next_pow2(DFD_NUM_VCS * glb_chunks);
+    P->cap_tc = next_pow2(cn_chunks);                // terminal -> router chunks: the terminal's single VC
+    P->cap_tk = next_pow2(DFD_NUM_VCS * cn_chunks);  // terminal -> router credits: the router's terminal port has all VCs
+    if (std::max(std::max(P->cap_l, P->cap_g), P->cap_tk) > 2048)
+        return fail(e, "VC sizes / chunk_size allow more than 2048 chunks in flight on one link: not supported");
+    if (p.radix > 128) return fail(e, "router radix %d is larger than 128: not supported", p.radix);
+    if (p.radix != P->ext + p.num_cn) return fail(e, "radix %d != local + global + terminal ports", p.radix);
+    if ((unsigned long long)p.total_routers * p.lps_per_rep >= (1ull << 30)) return fail(e, "more than 2^30 LPs: not supported");
+    P->cslots = p.intra_grp_radix * P->cap_l + p.global_radix * P->cap_g + p.num_cn * P->cap_tc;
+    P->kslots = p.intra_grp_radix * P->cap_l + p.global_radix * P->cap_g + p.num_cn * P->cap_tk;
+    // pool: pending chunks are bounded by the output VCs, overflowed (uncredited) ones by what the upstream links may have in flight
     long long in_chunks = (long long)p.intra_grp_radix * DFD_NUM_VCS * loc_chunks + (long long)p.global_radix * DFD_NUM_VCS * glb_chunks + (long long)p.num_cn * cn_chunks;
     long long out_chunks = (long long)p.intra_grp_radix * DFD_NUM_VCS * loc_chunks + (long long)p.global_radix * DFD_NUM_VCS * glb_chunks + (long long)p.num_cn * DFD_NUM_VCS * cn_chunks;
-    if (in_chunks > 65535 || out_chunks > 65535)
-        return fail(e, "VC sizes / chunk_size give more than 65535 chunks in flight per router (%lld in, %lld out): not supported", in_chunks, out_chunks);
-    P->rcin_cap = (int)in_chunks;
-    P->rkin_cap = (int)out_chunks;
+    if (in_chunks + out_chunks > (1 << 24)) return fail(e, "VC sizes / chunk_size give more than 2^24 chunks per router: not supported");
     P->rpool_cap = (int)(in_chunks + out_chunks);
-    // a sender never has more than VCs * vc_size / chunk_size uncredited chunks on one global link, and a link returns at
-    // most that many credits: no window can carry more records over it
-    P->xlane_cap = next_pow2(std::max(8, DFD_NUM_VCS * glb_chunks));
-    P->rheap_cap = (int)(in_chunks + out_chunks + p.radix + 1);
-    {   // timing wheel: must span the largest delay between a router event's creation and its timestamp
-        double maxbw_inj = std::max(h_bytes_to_ns(p.chunk_size, p.cn_bandwidth), std::max(h_bytes_to_ns(p.chunk_size, p.local_bandwidth), h_bytes_to_ns(p.chunk_size, p.global_bandwidth)));
-        double maxdelay = std::max(p.cn_delay, std::max(p.local_delay, p.global_delay));
-        double maxcredit = std::max(p.cn_credit_delay, std::max(p.local_credit_delay, p.global_credit_delay));
-        // A terminal may start a T_SEND while its link is still busy (packet_generate schedules it at +0 whenever the
-        // send loop is idle, dally:5749-5760), so terminal_available_time runs ahead of the clock by up to one
-        // injection time per chunk the VC can hold: the arrival at the first router lies that far in the future.
-        double term_ahead = (double)cn_chunks * h_bytes_to_ns(p.chunk_size, p.cn_bandwidth) + h_bytes_to_ns(p.chunk_size, p.cn_bandwidth) + p.cn_delay;
-        double span = std::max(std::max(2.0 * maxbw_inj + p.router_delay + maxdelay, term_ahead), maxcredit) + 2.0 * L;
-        const double bucket = 4.0 * L;  // bucket width: a window overlaps at most two buckets; 4x fewer heads to keep warm
-        double nb = span / bucket + 8.0;
-        if (nb > 1048576.0) return fail(e, "the ratio of the largest link delay (%g ns) to the lookahead window (%g ns) is too large for the timing wheel; set an explicit credit_delay", span, L);
-        P->wheel_nb = std::max(64, next_pow2((int)nb + 1));
-        P->inv_window = 1.0 / bucket;
+    {   // lower bounds of the serialisation time of any chunk this workload can emit (channel words, dfd_core.h): a chunk is
+        // chunk_size bytes, or a whole packet smaller than a chunk (packet sizes: the model-net packet size and the tail)
+        unsigned long long mb = (unsigned long long)p.chunk_size;
+        unsigned long long pay = (unsigned long long)o.payload_sz, mnp = p.mn_packet_size;
+        unsigned long long last = pay <= mnp ? pay : (pay % mnp ? pay % mnp : mnp);
+        if (pay > mnp) mb = std::min(mb, mnp);
+        mb = std::min(mb, last);
+        if (mb < 1) mb = 1;
+        P->lb_inj_term = h_bytes_to_ns(mb, p.cn_bandwidth);
+        P->lb_injrd_cn = h_bytes_to_ns(mb, p.cn_bandwidth) + p.router_delay;
+        P->lb_injrd_local = h_bytes_to_ns(mb, p.local_bandwidth) + p.router_delay;
+        P->lb_injrd_global = h_bytes_to_ns(mb, p.global_bandwidth) + p.router_delay;
     }
     return 0;
 }
@@ -1038,16 +1080,16 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
     bool reuse = e->device_ready && e->dev.X.rank == e->rank && e->dev.X.world == e->world && e->world == 1 && e->dev_ensemble == e->ensemble;
     if (reuse) {
         const DfdHostTopo& T = e->topo;
-        size_t tb = (T.loc_off.size() + T.loc_port.size() + T.loc_dest.size() + T.gs_port.size() + T.gs_group.size() + T.gdest.size() +
-                     T.routed_off.size() + T.routed_lid.size()) * sizeof(int);
-        reuse = tb == e->dev.topo_bytes;
+        const std::vector<int>* tabs[] = {&T.loc_off, &T.loc_port, &T.loc_dest, &T.lout_lane, &T.lin_src, &T.gs_port, &T.gs_group, &T.gdest, &T.gout_lane, &T.gin_src, &T.gin_port, &T.routed_off, &T.routed_lid};
+        reuse = e->dev.topo_sizes.size() == sizeof tabs / sizeof tabs[0];
+        for (size_t i = 0; reuse && i < e->dev.topo_sizes.size(); i++) reuse = tabs[i]->size() == e->dev.topo_sizes[i];  // every table, not the total
     }
     if (reuse) {
         const DfdParams& Q = e->dev.P;
         reuse = Q.NT == P.NT && Q.NR == P.NR && Q.radix == P.radix && Q.a == P.a && Q.p == P.p && Q.G == P.G && Q.h == P.h &&
                 Q.ncin_cap == P.ncin_cap && Q.nkin_cap == P.nkin_cap && Q.nsq_cap == P.nsq_cap && Q.ntq_cap == P.ntq_cap &&
-                Q.nev_cap == P.nev_cap && Q.nreasm_cap == P.nreasm_cap && Q.rcin_cap == P.rcin_cap && Q.rkin_cap == P.rkin_cap &&
-                Q.rpool_cap == P.rpool_cap && Q.xlane_cap == P.xlane_cap && Q.rheap_cap == P.rheap_cap && Q.wheel_nb == P.wheel_nb;
+                Q.nev_cap == P.nev_cap && Q.nreasm_cap == P.nreasm_cap && Q.cap_l == P.cap_l && Q.cap_g == P.cap_g &&
+                Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap;
     }
     if (reuse) {
         e->dev.P = P;
@@ -1058,7 +1100,11 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
         }
         e->dev = DfdDevice();
         seed_consts(&e->dev.seeds);
-        if (dfd_device_create(&e->dev, P, e->topo, e->rank, e->world, e->ensemble)) return fail(e, "%s", e->dev.error);
+        if (dfd_device_create(&e->dev, P, e->topo, e->rank, e->world, e->ensemble)) {
+            std::string msg = e->dev.error;
+            dfd_device_destroy(&e->dev);  // frees what a create that failed midway had already allocated
+            return fail(e, "%s", msg.c_str());
+        }
         e->dev_ensemble = e->ensemble;
         e->device_ready = true;
     }
@@ -1080,13 +1126,13 @@ int dfd_engine_reset(dfd_engine* e, void* stream) {
 
 int dfd_engine_run(dfd_engine* e, void* stream) {
     if (!e->uploaded) return fail(e, "engine_run: engine_upload has not been called");
-    if (dfd_device_run(&e->dev, (cudaStream_t)stream, ~0ULL >> 1)) return fail(e, "%s", e->dev.error);
+    if (dfd_device_run(&e->dev, (cudaStream_t)stream)) return fail(e, "%s", e->dev.error);
     return 0;
 }
 
 static void fill_summary_meta(dfd_engine* e) {
     dfd_summary& S = e->sum;
-    S.window_ns = e->dev.P.window;
+    S.window_ns = e->dev.P.min_delay;
     S.h2d_bytes = e->h2d_bytes;
     S.d2h_bytes = e->res.d2h_bytes;
     S.device_bytes = e->dev.bytes_allocated;
@@ -1096,65 +1142,23 @@ static void fill_summary_meta(dfd_engine* e) {
     S.num_terminals = e->hp.total_terminals;
     S.num_routers = e->hp.total_routers;
     S.radix = e->hp.radix;
-    S.cyc_scan = (double)e->res.counters[20] / e->dev.grid;
-    S.cyc_process = (double)e->res.counters[21] / e->dev.grid;
-    S.cyc_barrier = (double)e->res.counters[22] / e->dev.grid;
-    S.cyc_process_max_block = (double)e->res.counters[23];
-    S.cyc_process_longest = (double)e->res.counters[24];
+    const unsigned long long* C = e->res.counters;
+    S.cyc_busy = (double)C[20] / e->dev.grid;
+    S.cyc_idle = (double)C[21] / e->dev.grid;
+    S.cyc_busy_max_warp = (double)C[24];
+    S.activations = C[22];
+    S.passes = C[23];
 }
 
 static void profile_print(dfd_engine* e) {
     if (!getenv("DFD_PROFILE_PRINT")) return;
-    if (getenv("DFD_PROFILE2")) {  // -DDFD_PROFILE2 build: which router activations are the slowest of their window
-        std::map<unsigned, std::pair<unsigned long long, double>> pat;
-        unsigned long long nwin = 0;
-        double total = 0;
-        for (unsigned long long v : e->res.winmax) {
-            if (!v) continue;
-            auto& q = pat[(unsigned)(v & 0xFFFFFFFFu)];
-            q.first++;
-            q.second += (double)(v >> 32);
-            total += (double)(v >> 32);
-            nwin++;
-        }
-        std::vector<std::pair<double, unsigned>> order;
-        for (auto& kv : pat) order.push_back({kv.second.second, kv.first});
-        std::sort(order.rbegin(), order.rend());
-        fprintf(stderr, "  slowest router activation per window (cycles after the drain): %llu windows, mean %.0f cycles\n", nwin, total / std::max(1ULL, nwin));
-        for (size_t i = 0; i < order.size() && i < 24; i++) {
-            unsigned k = order[i].second;
-            auto& q = pat[k];
-            char seq[16] = {0};
-            unsigned n = (k >> 20) & 15;
-            for (unsigned j = 0; j < n && j < 10; j++) seq[j] = " ABS"[(k >> (2 * j)) & 3];  // A arrive, B buffer, S send
-            fprintf(stderr, "    drained %2u chunks %2u credits, events %-10s : %6llu windows (%4.1f%% of the cycles), mean %6.0f cycles\n", (k >> 28) & 15, (k >> 24) & 15,
-                    seq, q.first, 100.0 * q.second / total, q.second / q.first);
-        }
-        return;
-    }
     const unsigned long long* C = e->res.counters;
     const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
     for (int i = 0; i < EV_NTYPES; i++)
-        if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu  cycles/event %8.0f\n", names[i], C[4 + i], (double)C[32 + i] / C[4 + i]);
-    if (C[49]) fprintf(stderr, "  node activations %llu, cycles/activation %.0f\n", C[49], (double)C[48] / C[49]);
-    double sum[4] = {0, 0, 0, 0}, sumev[4] = {0, 0, 0, 0};
-    unsigned long long cnt[4] = {0, 0, 0, 0};
-    for (unsigned long long v : e->res.winmax) {
-        if (!v) continue;
-        int k = (int)(v & 3);
-        sum[k] += (double)(v >> 16);
-        sumev[k] += (double)((v >> 8) & 0xFF);
-        cnt[k]++;
-    }
-    const char* kn[4] = {"node", "router", "?", "router+drain"};
-    for (int k = 0; k < 4; k++)
-        if (cnt[k]) fprintf(stderr, "  slowest activation of the window is a %-12s in %6llu windows: avg %.0f cycles, %.1f events\n", kn[k], cnt[k], sum[k] / cnt[k], sumev[k] / cnt[k]);
-    if (C[4 + 11]) {
-        const char* st[6] = {"pop", "load chunk + route", "load port, next stop", "credit send", "enqueue + schedule R_SEND", "write back"};
-        for (int k = 0; k < 6; k++) fprintf(stderr, "  R_ARRIVE stage %-26s %7.0f cycles\n", st[k], (double)C[58 + k] / C[4 + 11]);
-    }
-    if (C[57]) fprintf(stderr, "  drained records %llu, cycles/record %.0f\n", C[57], (double)C[56] / C[57]);
-    if (C[51]) fprintf(stderr, "  router activations %llu (%llu with inbox drain), cycles/activation %.0f\n", C[51], C[52], (double)C[50] / C[51]);
+        if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu\n", names[i], C[4 + i]);
+    fprintf(stderr, "  warps %d, passes %llu, activations past the poll %llu, productive %llu, events/productive activation %.2f\n", e->dev.grid, C[23], C[22], C[1],
+            C[1] ? (double)C[0] / C[1] : 0.0);
+    fprintf(stderr, "  cycles per warp: busy passes %.0f, idle passes %.0f, busiest warp %.0f\n", (double)C[20] / e->dev.grid, (double)C[21] / e->dev.grid, (double)C[24]);
 }
 
 int dfd_engine_finish(dfd_engine* e, void* stream) {
@@ -1248,9 +1252,16 @@ int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
     PartHeader h;
     memcpy(&h, p, sizeof h);
     p += sizeof h;
-    size_t nn = h.n1 - h.n0, nr = h.r1 - h.r0, radix = e->hp.radix;
-    if (h.radix != (int)radix || h.n1 > e->hp.total_terminals || h.r1 > e->hp.total_routers || h.rank == e->rank)
-        return fail(e, "import_partition: partition does not belong to this run");
+    const size_t radix = e->hp.radix;
+    if (h.radix != (int)radix || h.rank < 0 || h.rank >= e->world || h.rank == e->rank) return fail(e, "import_partition: partition does not belong to this run");
+    {   // the blob must be exactly the partition of h.rank
+        DfdPeers Y;
+        dfd_partition(e->hp.num_groups, e->hp.num_routers, e->hp.num_cn, h.rank, e->world, &Y);
+        if (h.n0 != Y.n0 || h.n1 != Y.n1 || h.r0 != Y.r0 || h.r1 != Y.r1) return fail(e, "import_partition: bounds do not match the partition of rank %d", h.rank);
+    }
+    const size_t nn = (size_t)(h.n1 - h.n0), nr = (size_t)(h.r1 - h.r0);
+    const size_t need = sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) + nr * (sizeof(RouterHdr) + radix * sizeof(PortState));
+    if ((size_t)len < need) return fail(e, "import_partition: truncated buffer (%lld bytes, need %zu)", len, need);
     if (h.counters[2]) return fail(e, "rank %d reported device error %llu (%s)", h.rank, h.counters[2], device_error_name(h.counters[2]));
 #define GET(vec, off, cnt)                                   \
     memcpy((vec).data() + (off), p, (cnt) * sizeof((vec)[0])); \
@@ -1263,6 +1274,7 @@ int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
     GET(e->res.port, (size_t)h.r0 * radix, nr * radix)
 #undef GET
     e->res.counters[0] += h.counters[0];  // committed events
+    e->res.counters[1] += h.counters[1];
     for (int i = 0; i < EV_NTYPES; i++) e->res.counters[4 + i] += h.counters[4 + i];
     return 0;
 }

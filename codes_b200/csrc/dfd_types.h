@@ -1,5 +1,14 @@
-// Shared host/device data layout of the dragonfly-dally window engine.
+// Shared host/device data layout of the asynchronous dragonfly-dally engine.
 // Terminology follows the reference (terminal, router, chunk, credit, VC, port).
+//
+// Scheduling unit ("group"): one router LP plus the p compute nodes (svr + base LP + terminal, fused) that hang off
+// it, owned by one warp.  LPs talk through single-writer FIFO lanes, one per directed link and record kind:
+//   chunk lane  (u, port q) -> in-lane s of router d : 96-byte ChunkRec ring at d, written by u only
+//   credit lane  d -> port q of router u              : 16-byte Key ring at u, written by d only
+// Records of one lane are pushed in increasing (ts, src, seq) order (a port serialises its chunks, credits leave at
+// the sender's event times plus a constant), so a router's pending events are the heads of its lanes plus one R_SEND
+// timer per port.  Next to every lane the producer publishes a CHANNEL WORD: a lower bound on the timestamp of any
+// record it has not pushed yet, with the lane's record count stamped into the low bits (one 8-byte store is both).
 #pragma once
 #include <stdint.h>
 #include <vector_types.h>
@@ -30,9 +39,18 @@ enum { DFD_HOP_GLOBAL = 1, DFD_HOP_LOCAL = 2, DFD_HOP_TERMINAL = 3 };
 enum { DFD_SCORE_ALPHA = 1, DFD_SCORE_DELTA = 4 };
 enum { DFD_TR_UNIFORM = 1, DFD_TR_RAND_PERM = 2, DFD_TR_NEAREST_GROUP = 3, DFD_TR_NEAREST_NEIGHBOR = 4, DFD_TR_RANDOM_OTHER_GROUP = 5 };
 
+// event key: timestamp + deterministic tie-break (sender gid, sender's event-creation sequence number).
+// Also the 16-byte credit record (T_BUFFER / R_BUFFER): the receiving port is the lane, the VC rides in the two top
+// bits of src (gids are < 2^30).
+struct __attribute__((aligned(16))) Key {
+    double ts;
+    uint32_t src;
+    uint32_t seq;
+};
+#define DFD_GID_MASK 0x3FFFFFFFu
+
 // 96-byte packed chunk event (R_ARRIVE / T_ARRIVE): the fields of terminal_dally_message
-// (codes/net/dragonfly-dally.h:19-139) that are consumed downstream.  The first 16 bytes are the
-// event key (timestamp + deterministic tie-break: sender gid, sender's event-creation sequence).
+// (codes/net/dragonfly-dally.h:19-139) that are consumed downstream.  The first 16 bytes are the event key.
 struct __attribute__((aligned(16))) ChunkRec {
     double ts;
     uint32_t src;  // gid of the sending LP
@@ -64,27 +82,16 @@ struct __attribute__((aligned(16))) ChunkRec {
     uint32_t dst_router;  // router of dst_term
 };
 
-// 32-byte credit event (T_BUFFER / R_BUFFER)
-struct __attribute__((aligned(16))) CreditRec {
-    double ts;
-    uint32_t src;
-    uint32_t seq;
-    uint16_t port;  // vc_index at the receiver (its output port)
-    uint8_t vc;     // output_chan
-    uint8_t pad0;
-    uint32_t pad1;
-    uint64_t pad2;
-};
-
-// router chunk pool slot: a chunk waiting in pending_msgs / queued_msgs (or in flight towards the
-// router: copied here when the inbox is drained).  Same 96 bytes; the key bytes are reused.
+// router chunk pool slot: a chunk waiting in pending_msgs / queued_msgs.  Same 96 bytes as ChunkRec from offset 16
+// on; the key bytes are reused for the list link and the routing decision.
 struct __attribute__((aligned(16))) PoolSlot {
     uint32_t next;        // FIFO link / free-list link
     uint16_t out_port;    // vc_index chosen by this router
     uint8_t out_vc;       // output_chan chosen by this router
     uint8_t next_is_term; // next stop is the destination terminal
     uint32_t next_stop;   // router id or terminal id
-    uint32_t pad;
+    uint16_t in_lane;     // in-lane of this router the chunk arrived on (its credit goes back there)
+    uint16_t pad;
     uint32_t packet_id, src_term, dst_term, message_id;
     uint32_t packet_size, total_size;
     uint16_t chunk_id, dst_grp;
@@ -103,18 +110,6 @@ struct __attribute__((aligned(16))) PoolSlot {
     double msg_start_time;
     uint32_t origin_router, src_svr, dst_svr, dst_router;
 };
-
-// A router's pending events (chunk arrivals, credits, its own R_SEND timers) sit in a timing wheel: bucket
-// b = floor(ts / (4 * window)) mod wheel_nb holds a singly linked list of entries; a bitmap marks non-empty buckets.
-// Push is O(1); a window [T, T+L) only has to look at the (at most three) buckets it overlaps.
-struct __attribute__((aligned(8))) PendEnt {
-    double ts;
-    uint32_t src;
-    uint32_t seq;
-    uint32_t ref;   // kind<<28 | payload (pool slot / port | vc<<16)
-    uint32_t next;  // next entry of the bucket, or of the free list
-};
-enum { RK_CHUNK = 1, RK_CREDIT = 2, RK_SEND = 3 };
 
 // 64-byte hot state of one router output port (router_state dally:822-888)
 struct __attribute__((aligned(16))) PortState {
@@ -136,17 +131,29 @@ struct __attribute__((aligned(16))) PortQ {
     uint32_t queue_head[DFD_NUM_VCS], queue_tail[DFD_NUM_VCS];
 };
 
+// Lane cursors of a router, one entry per index j, read as in-lane j (chunks arriving) and as port j (credits
+// arriving, chunks leaving).  All counters count records modulo 2^16; a ring index is counter & (capacity - 1).
+struct __attribute__((aligned(16))) LaneCtl {
+    uint16_t chead, ctail;  // chunk in-lane j: records consumed / records known to be there
+    uint16_t khead, ktail;  // credit lane of port j
+    uint16_t sent_c;        // chunks this router pushed out of port j
+    uint16_t sent_k;        // credits this router pushed back on in-lane j
+    uint32_t pad;
+};
+
 struct __attribute__((aligned(16))) RouterHdr {
     int32_t rng[4];  // CLCG4 stream gid*3+0
     uint32_t seq;
-    uint32_t pend_n;     // pending events (entries in the wheel)
     uint32_t pool_nfree; // entries on the free-slot stack
     uint32_t gid;        // codes_mapping gid of this router
     uint16_t lid, grp;   // id inside the group, group id
-    uint32_t ent_nfree;  // entries on the free wheel-entry stack
-    uint32_t pad0, pad1;
-    double wmin;         // exact earliest timestamp among the wheel entries (+inf when the wheel is empty)
+    double clock;        // lower bound on the timestamp of this router's next event (< 0: never activated)
+    double last_ts;      // key of the last executed event (causality check)
+    uint32_t last_src, last_seq;
     unsigned long long rng_draws;
+    uint32_t more;       // the last activation stopped on its event budget: safe events may remain
+    uint32_t pad0;
+    unsigned long long activations;  // activations that executed at least one event
 };
 
 // self-scheduled event of a node (svr + base LP + terminal fused), 48 bytes
@@ -168,6 +175,16 @@ struct SchedReq {
     uint32_t msg_size;
     uint32_t rem;
     uint32_t msg_id;
+    double msg_start_time;
+};
+// A message between the two stages of handle_new_msg (model-net-lp.c:706-716): the second MN_BASE_NEW_MSG is
+// scheduled at next_available_time, which only grows, so these events form a FIFO of their own.
+struct MsgReq {
+    double ts;
+    uint32_t seq;
+    uint32_t dst_svr;
+    uint32_t msg_size;
+    uint32_t pad;
     double msg_start_time;
 };
 // one chunk waiting in terminal_msgs (dally:5653-5680), 40 bytes
@@ -203,7 +220,7 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t in_send_loop, issueIdle;
     uint32_t tq_head, tq_count;  // terminal_msgs ring
     uint32_t nev;                // number of pending self events
-    uint32_t cin_head, kin_head;
+    uint32_t cin_head, kin_head; // records consumed from the chunk / credit ring
     uint32_t grp;        // group of `router`
     double terminal_available_time, last_buf_full, busy_time;
     unsigned long long link_traffic, total_msg_size;
@@ -222,7 +239,9 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t svr_gid, term_gid;
     uint32_t mt_n, pt_n;  // live entries of the message / packet reassembly tables
     double node_copy_next_available_time;  // model_net_base_state.node_copy_next_available_time[0] (model-net-lp.c:672-704)
-    double pad_d;
+    uint32_t mq_head, mq_count;  // FIFO of second-stage MN_BASE_NEW_MSG events
+    double last_ts;              // key of the last executed event (causality check)
+    uint32_t last_src, last_seq;
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)
@@ -237,103 +256,126 @@ struct DfdParams {
     double cn_credit, local_credit, global_credit;
     int credit_size;
     double nic_seq_delay, lookahead, codes_cn_delay;
-    double window, ts_end;
+    double min_delay, ts_end;  // smallest cross-LP delay (a credit delay by default); end of the simulation
     // host-precomputed values of bytes_to_ns()/reciprocals (same IEEE operations as the device would do)
     double inj_chunk_cn, inj_chunk_local, inj_chunk_global;  // bytes_to_ns(chunk_size, bw)
     double inj_pay_cn, inj_pay_local, inj_pay_global;        // bytes_to_ns(payload_sz % chunk_size, bw)
     double inj_packet_cn;                                    // bytes_to_ns(payload_sz, cn_bw) (nic_ts of packet_generate)
     double inv_cn_bw;                                        // 1 / cn_bandwidth
+    // lower bounds used by the channel words: the smallest serialisation time any chunk of this workload can have on
+    // a link of each kind (plus router_delay for router ports, added first as router_packet_send does)
+    double lb_injrd_cn, lb_injrd_local, lb_injrd_global;     // router port: min injection delay + router_delay
+    double lb_inj_term;                                      // terminal NIC: min injection delay
     unsigned long long magic_p, magic_a;                     // floor(2^64/d)+1: n/d == __umul64hi(n, magic) for n < 2^32, d > 1
     int traffic, num_msgs, payload_sz;
     long long rperm_threshold;
     double warm_up_time, mean_interval;
     int num_nodes, nodes_per_grp, node_eager_limit, noop_bypass;
     int lps_per_rep, off_svr, off_term, off_rtr;
-    // ring capacities (powers of two) and heap/pool capacities
+    // ring capacities (powers of two) and pool capacities
     int ncin_cap, nkin_cap, nsq_cap, ntq_cap, nev_cap;
     int nreasm_cap;  // per-terminal reassembly table entries (0: every message is one chunk)
-    int rcin_cap, rkin_cap, rpool_cap, rheap_cap;
-    int xlane_cap;   // records one cross-GPU global link can carry per window and direction (chunks and credits each)
-    int wheel_nb;        // buckets of a router's timing wheel (power of two, >= max event delay / window + slack)
-    double inv_window;   // 1 / (wheel bucket width)
+    int cap_l, cap_g, cap_tc, cap_tk;  // lane capacities: local link, global link, terminal -> router chunks, terminal -> router credits
+    int cslots, kslots;                // records per router in ring_c / ring_k
+    int rpool_cap;
+    int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
 };
 
-// device arrays
+struct DfdSeedConsts {  // CLCG4 constants: moduli, default seed, a^(2^(31+41)) mod m (stream jump)
+    unsigned long long m[4], seed0[4], avw[4];
+};
+
+// run control block at the start of every rank's exchange region; rank 0's copy carries the global counters
+// Termination: `created` counts the events this rank brought into being (self events, timers, records pushed to any
+// rank; added BEFORE the release fence that publishes them), `consumed` the events it executed (added after that
+// fence).  Both only grow.  A monitor that reads every rank's `consumed` first and every rank's `created` afterwards
+// and finds the sums equal has seen a moment with nothing pending anywhere: the simulation is over.
+struct DfdCtrl {
+    unsigned long long created;
+    unsigned long long consumed;
+    unsigned long long error;     // first device error code (other ranks receive DFD_ERR_PEER_ERROR)
+    unsigned long long error_info;
+    unsigned long long done;      // set by this rank's monitor warp
+    unsigned long long pad[27];
+};
+
+// device arrays.  Everything indexed by router / node uses the LOCAL index inside this rank's partition.
 struct DfdArrays {
-    // wake times (IEEE doubles compared as uint64: all timestamps are >= 0)
-    unsigned long long* wake_self;  // [NLP]
-    unsigned long long* wake_in;    // [2][NLP]
-    unsigned long long* gmin;       // [3]
     // nodes
-    NodeState* node;        // [NT]
-    NodeEv* nev;            // [NT][nev_cap]
-    SchedReq* sq;           // [NT][nsq_cap]
-    TermChunk* tq;          // [NT][ntq_cap]
-    ChunkRec* ncin;         // [NT][ncin_cap]
-    CreditRec* nkin;        // [NT][nkin_cap]
-    uint4* mtab;            // [NT][nreasm_cap] rank_tbl: {message_id, sender svr, remaining_packets, has_remote}
-    uint4* ptab;            // [NT][nreasm_cap] remaining_sz_packets: {packet_id, source terminal, remaining bytes, -}
-    unsigned* ncin_tail;    // [NT]
-    unsigned* nkin_tail;    // [NT]
-    unsigned* ack_count;             // [NT]
-    unsigned long long* ack_first;   // [NT]
-    unsigned long long* ack_last;    // [NT]
-    // routers
-    RouterHdr* rh;        // [NR]
-    PortState* port;      // [NR][radix]
-    PortQ* portq;         // [NR][radix]
-    PoolSlot* pool;       // [NR][rpool_cap]
-    PendEnt* pent;               // [NR][rheap_cap]   wheel entries
-    unsigned* pfree;             // [NR][rpool_cap]   stack of free pool slots
-    unsigned* efree;             // [NR][rheap_cap]   stack of free wheel entries
-    unsigned* wheel;             // [NR][wheel_nb]    bucket heads
-    unsigned long long* wbits;   // [NR][wheel_nb/64] non-empty-bucket bitmap
-    // cross-GPU global links (world > 1): one single-writer lane per (router, global port) and window parity
-    ChunkRec* xc;                // [2][NR][h][xlane_cap]
-    CreditRec* xk;               // [2][NR][h][xlane_cap]
-    unsigned* xcnt;              // [2][NR][h]  chunks | credits << 16 written into the lane this window
-    unsigned long long* xmask;   // [2][NR]     bit k: lane k holds records
-    uint2* xsend;                // [NR][h]     sender side: {window stamp, packed counts} of the lane behind my port
-    const int* grev;             // [NR][h]     far-end global-port index of each global link
-    ChunkRec* rcin;       // [NR][rcin_cap]
-    CreditRec* rkin;      // [NR][rkin_cap]
-    unsigned* rcin_tail;  // [NR]
-    unsigned* rkin_tail;  // [NR]
-    // topology (read-only)
+    NodeState* node;        // [NTl]
+    NodeEv* nev;            // [NTl][nev_cap]
+    SchedReq* sq;           // [NTl][nsq_cap]
+    MsgReq* mq;             // [NTl][nsq_cap]
+    TermChunk* tq;          // [NTl][ntq_cap]
+    ChunkRec* ncin;         // [NTl][ncin_cap]   router -> terminal chunks
+    Key* nkin;              // [NTl][nkin_cap]   router -> terminal credits
+    uint4* mtab;            // [NTl][nreasm_cap] rank_tbl: {message_id, sender svr, remaining_packets, has_remote}
+    uint4* ptab;            // [NTl][nreasm_cap] remaining_sz_packets: {packet_id, source terminal, remaining bytes, -}
+    unsigned* ncin_tail;    // [NTl]
+    unsigned* nkin_tail;    // [NTl]
+    unsigned* ack_count;             // [NTmax] exchange region
+    unsigned long long* ack_first;   // [NTmax]
+    unsigned long long* ack_last;    // [NTmax]
+    // routers: private state
+    RouterHdr* rh;        // [NRl]
+    PortState* port;      // [NRl][radix]
+    PortQ* portq;         // [NRl][radix]
+    Key* skey;            // [NRl][radix]  pending R_SEND of the port (ts = +inf: none)
+    Key* ckey;            // [NRl][radix]  head of chunk in-lane j, or {bound, 0, 0} while the lane is empty
+    Key* kkey;            // [NRl][radix]  head of the credit lane of port j, or {bound, 0, 0}
+    LaneCtl* lane;        // [NRl][radix]
+    unsigned long long* seen_c;  // [NRl][radix] channel words as last polled
+    unsigned long long* seen_k;
+    unsigned long long* pub_c;   // [NRl][radix] channel words as last published
+    unsigned long long* pub_k;
+    unsigned char* nq;           // [NRl][radix][radix] overflowed (queued_msgs) chunks by (in-lane, out port)
+    unsigned long long* qbits;   // [NRl][radix][2]     bit q of in-lane s: nq[s][q] > 0
+    double* iblk;                // [NRl][2][p]         bounds of the terminal lanes (chunks, credits) for the router phase
+    PoolSlot* pool;       // [NRl][rpool_cap]
+    unsigned* pfree;      // [NRl][rpool_cap]   stack of free pool slots
+    // routers: exchange region (written by neighbours, possibly from another GPU)
+    unsigned long long* cw_c;    // [NRmax][radix] chunk channel words (by in-lane)
+    unsigned long long* cw_k;    // [NRmax][radix] credit channel words (by port)
+    ChunkRec* ring_c;            // [NRmax][cslots]
+    Key* ring_k;                 // [NRmax][kslots]
+    DfdCtrl* ctrl;
+    // topology (read-only, global router ids)
     const int* loc_off;     // [a*a+1]   CSR over (my lid, dest lid) -> local ports
     const int* loc_port;    // [..]
     const int* loc_dest;    // [a][intra_radix] destination local id of local port j of local router i
+    const int* lout_lane;   // [a][intra_radix] in-lane of that destination my local port feeds
+    const int* lin_src;     // [a][intra_radix] in-lane s of local router i: source lid << 16 | its port, or -1
     const int* gs_port;     // [NR][h]   global ports in by-dest-gid order (get_connections_by_type)
     const int* gs_group;    // [NR][h]   destination group of gs_port
     const int* gdest;       // [NR][h]   destination router of global port intra_radix+i
+    const int* gout_lane;   // [NR][h]   in-lane (absolute index) of that destination my global port feeds
+    const int* gin_src;     // [NR][h]   source router of global in-lane intra_radix+i, or -1
+    const int* gin_port;    // [NR][h]   its (absolute) port
     const int* routed_off;  // [G*G+1]   CSR over (src group, dest group)
     const int* routed_lid;  // [..]      local id of the router owning each global link, inter-file order
     // run control / results
-    unsigned long long* counters;  // [64]: 0 events, 1 windows, 2 error code, 3 error info, 4.. per-type, 20.. cycles
-    unsigned long long* winmax;    // [65536] profile builds: slowest LP activation of each window
+    unsigned long long* counters;  // [64]: 0 events, 1 productive activations, 2 error code, 3 error info, 4.. per-type, 20.. cycles
 };
 
 // Group-sharded multi-GPU run: rank k owns the dragonfly groups [grp_lo[k], grp_lo[k+1]) with all
 // their routers, terminals and servers.  Only three things cross ranks: chunks and credits over global links
-// (written straight into the owner's router inbox through a CUDA-IPC mapping of its exchange region) and the
-// svr->svr ACK statistics.  One window = local grid barrier, flag + minimum exchange over NVLink, local barrier.
+// (records and channel words written straight into the owner's exchange region through a CUDA-IPC mapping) and the
+// svr->svr ACK statistics.  There is no barrier and no collective: a router that owns a global link simply sees its
+// peer's channel word like any other neighbour's.
 #define DFD_MAX_RANKS 8
-// lives at the start of every rank's exchange region.  mins[w%3][k]: rank k's earliest pending timestamp for
-// window w, written by rank k when it closes window w-1; DFD_SYNC_EMPTY until then, DFD_SYNC_FAILED if rank k
-// raised a device error.
-struct DfdSync {
-    unsigned long long mins[3][DFD_MAX_RANKS];
-};
-#define DFD_SYNC_EMPTY 0xFFFFFFFFFFFFFFFFULL
-#define DFD_SYNC_FAILED 0xFFFFFFFFFFFFFFFEULL
 struct DfdPeers {
     int rank, world;
     int grp_lo[DFD_MAX_RANKS + 1];
-    int n0, n1, r0, r1;                 // owned node / router ranges
+    int n0, n1, r0, r1;                 // owned node / router ranges (global ids)
     char* base[DFD_MAX_RANKS];          // exchange-region base of every rank as mapped into this process
     char* local_base;                   // == base[rank]
 };
 
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,
        DFD_ERR_HEAP_OVERFLOW, DFD_ERR_INBOX_OVERFLOW, DFD_ERR_DEAD_END, DFD_ERR_WRONG_TERMINAL, DFD_ERR_BAD_VC, DFD_ERR_SELF_SEND,
-       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR, DFD_ERR_REASM_OVERFLOW, DFD_ERR_WHEEL_RANGE };
+       DFD_ERR_LATE_EVENT, DFD_ERR_PEER_TIMEOUT, DFD_ERR_PEER_ERROR, DFD_ERR_REASM_OVERFLOW, DFD_ERR_WHEEL_RANGE, DFD_ERR_STALL };
+
+// channel words: the low DFD_STAMP_BITS of the bound's bit pattern are replaced by the lane's record count
+#define DFD_STAMP_BITS 12
+#define DFD_STAMP_MASK 0xFFFULL
+#define DFD_TS_BIG 1e300  // "never": a finite stand-in for +inf that survives stamping

@@ -38,7 +38,7 @@ typedef struct dfd_synthetic_opts {
 typedef struct dfd_summary {
     unsigned long long events;          /* "Net Events Processed": reference-equivalent committed events */
     unsigned long long events_by_type[16];
-    unsigned long long windows;         /* lookahead windows executed */
+    unsigned long long windows;         /* group activations that executed at least one event (the engine has no global windows) */
     long long total_hops, finished_packets, finished_msgs, finished_chunks, total_msg_sz;
     double total_time, max_latency;
     long long packet_gen, packet_fin, local_same_router, local_same_group, remote;
@@ -47,13 +47,15 @@ typedef struct dfd_summary {
     double svr_sum_latency, svr_max_latency, max_end_ts;
     double total_offered_load, total_observed_load;
     unsigned long long rng_draws;
-    double window_ns;                   /* lookahead window length */
+    double window_ns;                   /* smallest cross-LP delay of the configuration (a credit delay by default) */
     unsigned long long h2d_bytes, d2h_bytes, device_bytes;
     int grid_blocks, block_threads, num_sms;
     int num_terminals, num_routers, radix;
-    /* cycle accounting of the window kernel, averaged over blocks: scan / process / barrier wait per run, the
-     * largest per-block process total, and the longest single process phase */
-    double cyc_scan, cyc_process, cyc_barrier, cyc_process_max_block, cyc_process_longest;
+    /* cycle accounting of the event-loop kernel per warp: cycles spent in passes over its groups that executed
+     * events / that found nothing safe (averages over the warps), and the busiest warp's busy cycles */
+    double cyc_busy, cyc_idle, cyc_busy_max_warp;
+    unsigned long long activations;     /* activations that got past the channel-word poll */
+    unsigned long long passes;          /* passes of the warps over their groups */
 } dfd_summary;
 
 void dfd_synthetic_opts_default(dfd_synthetic_opts* o);
