@@ -118,7 +118,16 @@ DFD_FN int4 ld_cg16(const void* p) { return *(const int4*)p; }
 DFD_FN void st_cg16(void* p, int4 v) { *(int4*)p = v; }
 DFD_FN unsigned long long ld_strong64(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
 DFD_FN unsigned long long ld_strong64_sys(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
-DFD_FN void st_strong64(unsigned long long* p, unsigned long long v, bool) { *(volatile unsigned long long*)p = v; }
+// test hook (tests/cpusim, "synchronous rounds" mode): channel words published during a sweep become visible after it
+#include <utility>
+#include <vector>
+static std::vector<std::pair<unsigned long long*, unsigned long long>>* dfd_host_deferred_words = nullptr;
+DFD_FN void st_strong64(unsigned long long* p, unsigned long long v, bool) {
+    if (dfd_host_deferred_words)
+        dfd_host_deferred_words->push_back(std::make_pair(p, v));
+    else
+        *(volatile unsigned long long*)p = v;
+}
 DFD_FN void fence_release(bool) {}
 DFD_FN void red_add_i64(long long* p, long long v, bool) { *p += v; }
 DFD_FN void ack_update(unsigned* cnt, unsigned long long* first, unsigned long long* last, unsigned long long tb, bool) {
@@ -172,24 +181,32 @@ DFD_FN Key key_from_int4(int4 v) {
     return k;
 }
 
-// warp-wide argmin of (key, idx): every lane contributes its local best, every lane receives the winner
+// warp-wide argmin of (key, idx): every lane contributes its local best, every lane receives the winner.
+// Timestamps are non-negative doubles, so their bit patterns order like unsigned integers: two 32-bit redux.min
+// steps settle almost every pick; equal timestamps fall through to sender gid, sequence number and index.
 DFD_FN void warp_argmin_key(Key& k, int& idx) {
 #ifdef __CUDACC__
-    for (int o = 16; o > 0; o >>= 1) {
-        double ts = __shfl_xor_sync(0xFFFFFFFFu, k.ts, o);
-        unsigned src = __shfl_xor_sync(0xFFFFFFFFu, k.src, o);
-        unsigned seq = __shfl_xor_sync(0xFFFFFFFFu, k.seq, o);
-        int oi = __shfl_xor_sync(0xFFFFFFFFu, idx, o);
-        // ties between different entries with an identical key cannot both be events (keys are unique); between two
-        // blockers any winner will do, but every lane must pick the same one: the smaller index
-        bool take = key_less(ts, src, seq, k.ts, k.src, k.seq) || (ts == k.ts && src == k.src && seq == k.seq && oi < idx);
-        if (take) {
-            k.ts = ts;
-            k.src = src;
-            k.seq = seq;
-            idx = oi;
-        }
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned long long tb = d2bits(k.ts);
+    const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+    const unsigned mhi = __reduce_min_sync(full, hi);
+    const bool in1 = hi == mhi;
+    const unsigned mlo = __reduce_min_sync(full, in1 ? lo : 0xFFFFFFFFu);
+    unsigned m = __ballot_sync(full, in1 && lo == mlo);
+    if (m & (m - 1)) {  // several lanes hold the same timestamp
+        bool in = (m >> DFD_LANE()) & 1u;
+        const unsigned msrc = __reduce_min_sync(full, in ? k.src : 0xFFFFFFFFu);
+        in = in && k.src == msrc;
+        const unsigned mseq = __reduce_min_sync(full, in ? k.seq : 0xFFFFFFFFu);
+        in = in && k.seq == mseq;
+        const unsigned midx = __reduce_min_sync(full, in ? (unsigned)idx : 0xFFFFFFFFu);
+        m = __ballot_sync(full, in && (unsigned)idx == midx);
     }
+    const int win = __ffs((int)m) - 1;
+    k.ts = __shfl_sync(full, k.ts, win);
+    k.src = __shfl_sync(full, k.src, win);
+    k.seq = __shfl_sync(full, k.seq, win);
+    idx = __shfl_sync(full, idx, win);
 #else
     (void)k;
     (void)idx;
@@ -228,11 +245,26 @@ struct Ctx {
     Key* ring_k;
     double* iblk;   // [2][p]: bounds of the (empty) terminal lanes, set at the start of every router phase
     double rclock;  // lower bound on the router's next event
+    bool nothing_pending;  // no event is pending anywhere in the group and no external lane has a finite bound
+    double node_floor;     // earliest pending event of any terminal of the group (as of the last bounds pass)
+    double node_push_min;  // earliest record the router handed to a terminal since then (lane 0)
     // --- per-lane accounting of this activation
     unsigned ncreated;  // events created
     unsigned nexec;     // events executed
     bool wrote_remote;  // pushed a record into another rank's memory
+    // --- cycle accounting of the activations of this warp (lane 0): poll, terminal bounds, router phase, node phase, publish
+    long long cyc[6];
+    unsigned long long nrounds;
 };
+#ifdef DFD_DEBUG_HOST
+#include <stdio.h>
+#include <stdlib.h>
+#endif
+#ifdef __CUDACC__
+#define CYC_NOW() clock64()
+#else
+#define CYC_NOW() 0LL
+#endif
 
 DFD_FN void set_error(const Ctx& c, unsigned code, unsigned long long info) {
     const DfdArrays& A = *c.A;
@@ -408,6 +440,7 @@ DFD_FN void push_chunk_to_node(Ctx& c, unsigned n, const ChunkRec& rec) {
 #pragma unroll
     for (int i = 0; i < 6; i++) dst[i] = src[i];
     c.ncreated++;
+    c.node_push_min = mind(c.node_push_min, rec.ts);
 }
 DFD_FN void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src, unsigned seq) {
     const DfdParams& P = *c.P;
@@ -417,6 +450,10 @@ DFD_FN void push_credit_to_node(Ctx& c, unsigned n, double ts, unsigned src, uns
     unsigned idx = A.nkin_tail[nl]++;
     A.nkin[(size_t)nl * P.nkin_cap + (idx & (P.nkin_cap - 1))] = mk_key(ts, src, seq);
     c.ncreated++;
+    c.node_push_min = mind(c.node_push_min, ts);
+#ifdef DFD_DEBUG_HOST
+    if (getenv("DFD_DBG_NODE") && (unsigned)atoi(getenv("DFD_DBG_NODE")) == n) fprintf(stderr, "  push credit to node %u ts=%.6f seq=%u (router clock %.6f)\n", n, ts, seq, c.rclock);
+#endif
 }
 // chunk / credit from terminal t of this group to its router (terminal lane ext + t; same warp)
 DFD_FN void node_push_chunk(Ctx& c, int t, const ChunkRec& rec) {
@@ -941,14 +978,19 @@ DFD_FN NodeBounds node_bounds(const Ctx& c, int t, unsigned nl, const NodeState*
     // router_packet_send towards the terminal: noat = max(noat, now) + (inj + router_delay); arrival = noat + cn_delay
     double st = ps.in_send_loop ? c.skey[s].ts : c.rclock;
     b.rb = lower((maxd(ps.noat, st) + P.lb_injrd_cn) + P.cn_delay);
-    const double S = node_self_next(P, A, nl, ns);
+    const double S = ns->self_next;
     const LaneCtl& L = c.lane[s];
-    // next R_ARRIVE of one of this terminal's chunks, ignoring T_SENDs that a credit could trigger: such a credit
-    // cannot come before kb itself ("credit bound of a terminal lane")
-    double a_in = L.chead != L.ctail ? c.ckey[s].ts : lower((maxd(ns->terminal_available_time, S) + P.lb_inj_term) + P.cn_delay);
+    // Credits already waiting in the terminal's ring, and the next self event: what can start a T_SEND before any
+    // further credit arrives (terminal_buf_update only restarts the send loop while chunks are waiting).
+    const unsigned ktail = A.nkin_tail[nl];
+    const bool kr_ne = ns->kin_head != ktail;
+    const double khead = kr_ne ? A.nkin[(size_t)nl * P.nkin_cap + (ns->kin_head & (P.nkin_cap - 1))].ts : DFD_TS_BIG;
+    const double trig0 = ns->tq_count > 0 ? mind(S, khead) : S;
+    // next R_ARRIVE of one of this terminal's chunks, ignoring T_SENDs triggered by credits that are not in the ring yet:
+    // such a credit cannot come before kb itself ("credit bound of a terminal lane")
+    double a_in = L.chead != L.ctail ? c.ckey[s].ts : lower((maxd(ns->terminal_available_time, trig0) + P.lb_inj_term) + P.cn_delay);
     b.kb = P.cn_credit + mind(a_in, late_credit_bound(c, s));
-    unsigned ktail = A.nkin_tail[nl];
-    double knext = ns->kin_head != ktail ? A.nkin[(size_t)nl * P.nkin_cap + (ns->kin_head & (P.nkin_cap - 1))].ts : b.kb;
+    double knext = kr_ne ? khead : b.kb;
     // a T_SEND needs a self event (T_GENERATE, a re-armed T_SEND) or, with chunks waiting, a credit (terminal_buf_update)
     double trig = ns->tq_count > 0 ? mind(S, knext) : S;
     b.x = lower((maxd(ns->terminal_available_time, trig) + P.lb_inj_term) + P.cn_delay);
@@ -1016,6 +1058,7 @@ DFD_FN_NOINLINE unsigned node_process(Ctx& c, int t, unsigned n, unsigned nl, do
                 bseq = mq->seq;
             }
         }
+        s->self_next = bts;  // exact whenever the loop is left: nothing is added to the lists outside this function
         double horizon = DFD_TS_BIG;
         const ChunkRec* ch = nullptr;
         if (s->cin_head != ctail) {
@@ -1041,6 +1084,10 @@ DFD_FN_NOINLINE unsigned node_process(Ctx& c, int t, unsigned n, unsigned nl, do
             horizon = mind(horizon, kb);
         if (!(bts < horizon)) break;
         double now = bts;
+#ifdef DFD_DEBUG_HOST
+        if (getenv("DFD_DBG_NODE") && (unsigned)atoi(getenv("DFD_DBG_NODE")) == n)
+            fprintf(stderr, "  node %u exec kind=%d key=(%.6f,%u,%u) rb=%.6f kb=%.6f horizon=%.6f rclock=%.6f tq=%u vc=%d\n", n, kind, bts, bsrc, bseq, rb, kb, horizon, c.rclock, s->tq_count, s->vc_occupancy);
+#endif
         check_order(c, &s->last_ts, &s->last_src, &s->last_seq, bts, bsrc, bseq, kind == 1 || kind == 2, 0x8000000000000000ULL | n);
         s->events++;
         nproc++;
@@ -1697,25 +1744,36 @@ DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
     for (;;) {
         Key best = mk_key(DFD_TS_BIG, 0xFFFFFFFFu, 0xFFFFFFFFu);
         int bidx = 3 * radix;
+        // `hard`: the same minimum without the bounds of empty TERMINAL lanes.  Those bounds are derived from the
+        // router's own clock and would let it creep upwards round by round; the next router event, however, can only
+        // come from a pending router event, an external lane, or an event pending at one of the terminals.
+        double hard = DFD_TS_BIG;
         LANE_FOR(j, radix) {
+            const LaneCtl L = c.lane[j];
+            const bool ext = j < P.ext;
             Key k = c.ckey[j];
             if (key_lt(k, best)) {
                 best = k;
                 bidx = j;
             }
+            if (ext || L.chead != L.ctail) hard = mind(hard, k.ts);
             k = c.kkey[j];
             if (key_lt(k, best)) {
                 best = k;
                 bidx = radix + j;
             }
+            if (ext || L.khead != L.ktail) hard = mind(hard, k.ts);
             k = c.skey[j];
             if (key_lt(k, best)) {
                 best = k;
                 bidx = 2 * radix + j;
             }
+            hard = mind(hard, k.ts);
         }
         warp_argmin_key(best, bidx);
-        c.rclock = best.ts;
+        hard = mind(warp_min_d(mind(hard, c.node_push_min)), c.node_floor);
+        c.rclock = maxd(best.ts, mind(hard, DFD_TS_BIG));
+        c.nothing_pending = !(hard < DFD_TS_BIG);
         if (bidx >= 3 * radix) break;
         int kind = bidx / radix, j = bidx - kind * radix;
         LaneCtl L = c.lane[j];
@@ -1797,15 +1855,41 @@ struct ActResult {
 };
 
 #ifndef DFD_ACT_BUDGET
-#define DFD_ACT_BUDGET 24  // events after which an activation publishes its bounds even if more would be safe
+#define DFD_ACT_BUDGET 4  // router events after which an activation publishes its bounds even if more would be safe
 #endif
+
+// earliest pending event of a terminal: self events and the heads of its two rings
+DFD_FN double node_next_pending(const Ctx& c, unsigned nl, const NodeState* ns) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    double next = ns->self_next;
+    if (ns->cin_head != A.ncin_tail[nl]) next = mind(next, A.ncin[(size_t)nl * P.ncin_cap + (ns->cin_head & (P.ncin_cap - 1))].ts);
+    if (ns->kin_head != A.nkin_tail[nl]) next = mind(next, A.nkin[(size_t)nl * P.nkin_cap + (ns->kin_head & (P.nkin_cap - 1))].ts);
+    return next;
+}
+
+// true when terminal t has an event it may execute now: its earliest pending timestamp lies below its horizon
+DFD_FN bool node_has_work(const Ctx& c, unsigned nl, const NodeState* ns, const NodeBounds& b) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    double next = ns->self_next, horizon = DFD_TS_BIG;
+    if (ns->cin_head != A.ncin_tail[nl])
+        next = mind(next, A.ncin[(size_t)nl * P.ncin_cap + (ns->cin_head & (P.ncin_cap - 1))].ts);
+    else
+        horizon = b.rb;
+    if (ns->kin_head != A.nkin_tail[nl])
+        next = mind(next, A.nkin[(size_t)nl * P.nkin_cap + (ns->kin_head & (P.nkin_cap - 1))].ts);
+    else
+        horizon = mind(horizon, b.kb);
+    return next < horizon;
+}
 
 // One activation of group rl.  Returns the number of events executed (0 when nothing was safe).
 DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const DfdPeers& X = *c.X;
-    ctx_bind_group(c, rl);
+    if (c.rl != rl || c.port == nullptr) ctx_bind_group(c, rl);
     c.ncreated = 0;
     c.nexec = 0;
     c.wrote_remote = false;
@@ -1813,7 +1897,8 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     res.nexec = 0;
     RouterHdr hd = A.rh[rl];  // lane 0's working copy; written back once
     // ---- (1) poll the channel words of the external lanes
-    bool changed = hd.more != 0 || hd.clock < 0.0;
+    const bool first = hd.clock < 0.0;
+    bool changed = hd.more != 0 || first;
     {
         const unsigned long long* cwc = A.cw_c + (size_t)rl * P.radix;
         const unsigned long long* cwk = A.cw_k + (size_t)rl * P.radix;
@@ -1853,6 +1938,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     res.polled_change = warp_any(changed);
     if (!res.polled_change) return res;  // the previous activation ran to its fixed point on exactly this input
     WARP_SYNC();
+    long long t0 = CYC_NOW(), t1;
     // ---- (2) rounds of router phase + node phase until nothing more is safe (or the event budget is spent)
     c.gid = hd.gid;
     c.lid = hd.lid;
@@ -1860,34 +1946,71 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     c.rclock = hd.clock < 0.0 ? 0.0 : hd.clock;
     const unsigned nbase = c.r * (unsigned)P.p;        // first node of the group (global id)
     const unsigned nlbase = nbase - (unsigned)X.n0;     // ... local index
-    unsigned total = 0;
-    bool more = true;
-    while (more && total < DFD_ACT_BUDGET) {
+    unsigned total = 0, nrouter = 0;
+    bool more = false;
+    for (;;) {
         const double clock_in = c.rclock;
+        c.nrounds++;
+        t1 = CYC_NOW();
+        c.cyc[0] += t1 - t0;
+        t0 = t1;
         // bounds of the terminal lanes as seen by the router
+        bool nwork = false;
+        double nfloor = DFD_TS_BIG;
         LANE_FOR(t, P.p) {
-            NodeBounds b = node_bounds(c, t, nlbase + t, &A.node[nlbase + t]);
+            const NodeState* ns = &A.node[nlbase + t];
+            NodeBounds b = node_bounds(c, t, nlbase + t, ns);
+            nfloor = mind(nfloor, node_next_pending(c, nlbase + t, ns));
             const int s = P.ext + t;
             c.iblk[t] = b.x;
             c.iblk[P.p + t] = b.y;
             LaneCtl L = c.lane[s];
             if (L.chead == L.ctail) c.ckey[s] = mk_key(b.x, 0, 0);
             if (L.khead == L.ktail) c.kkey[s] = mk_key(b.y, 0, 0);
+            nwork = nwork || node_has_work(c, nlbase + t, ns, b);
         }
+        c.node_floor = warp_min_d(nfloor);
+        c.node_push_min = DFD_TS_BIG;
         WARP_SYNC();
-        unsigned nr = router_phase(c, &hd, DFD_ACT_BUDGET - total);
+        t1 = CYC_NOW();
+        c.cyc[1] += t1 - t0;
+        t0 = t1;
+        unsigned nr = router_phase(c, &hd, DFD_ACT_BUDGET - nrouter);
+        nrouter += nr;
         WARP_SYNC();
+        t1 = CYC_NOW();
+        c.cyc[2] += t1 - t0;
+        t0 = t1;
         unsigned nn = 0;
-        LANE_FOR(t, P.p) {
-            NodeBounds b = node_bounds(c, t, nlbase + t, &A.node[nlbase + t]);
-            nn += node_process(c, t, nbase + t, nlbase + t, b.rb, b.kb);
+        // the router phase can only raise a terminal's horizon or hand it new records: without router events the
+        // terminals that had nothing to do before it still have nothing to do
+        if (nr != 0 || warp_any(nwork)) {
+            LANE_FOR(t, P.p) {
+                const NodeState* ns = &A.node[nlbase + t];
+                NodeBounds b = node_bounds(c, t, nlbase + t, ns);
+                if (node_has_work(c, nlbase + t, ns, b)) nn += node_process(c, t, nbase + t, nlbase + t, b.rb, b.kb);
+            }
+            WARP_SYNC();
         }
-        WARP_SYNC();
         c.nexec += nn;
         if (IS_LANE0()) c.nexec += nr;
         nn = warp_sum_u(nn);
         total += nr + nn;
-        more = (nr + nn) != 0 || c.rclock > clock_in;
+        t1 = CYC_NOW();
+        c.cyc[3] += t1 - t0;
+        t0 = t1;
+#ifdef DFD_DEBUG_HOST
+        {
+            static unsigned long long dbg_rounds = 0;
+            if (++dbg_rounds % 1000000 == 0)
+                fprintf(stderr, "rounds %llu r=%u nr=%u nn=%u rclock=%.6f clock_in=%.6f total=%u nrouter=%u\n", dbg_rounds, c.r, nr, nn, c.rclock, clock_in, total, nrouter);
+        }
+#endif
+        if ((nr + nn) == 0 && (!(c.rclock > clock_in) || c.nothing_pending)) break;  // fixed point
+        if (nrouter >= DFD_ACT_BUDGET) {  // publish what is known so far; the next pass continues
+            more = true;
+            break;
+        }
     }
     res.nexec = total;
     if (IS_LANE0()) {
@@ -1898,66 +2021,86 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     }
     c.h = &A.rh[rl];
     WARP_SYNC();
-    // ---- (3) publish: created count, one release fence, consumed count and the channel words
+    // ---- (3) publish: created count, one release fence, consumed count and the channel words.  Bounds alone need no
+    // fence: they only promise something about records that do not exist yet.
     const unsigned created = warp_sum_u(c.ncreated);
     const bool sys = X.world > 1;
-    if (IS_LANE0() && created) red_add_i64((long long*)&A.ctrl->created, (long long)created, sys);
-    fence_release(sys);
-    if (IS_LANE0() && total) red_add_i64((long long*)&A.ctrl->consumed, (long long)total, sys);
+    if (total | created) {
+        if (IS_LANE0() && created) red_add_i64((long long*)&A.ctrl->created, (long long)created, sys);
+        fence_release(sys);
+        if (IS_LANE0() && total) red_add_i64((long long*)&A.ctrl->consumed, (long long)total, sys);
+    }
     {
         unsigned long long* pubc = A.pub_c + (size_t)rl * P.radix;
         unsigned long long* pubk = A.pub_k + (size_t)rl * P.radix;
-        LANE_FOR(q, P.ext) {
-            // chunk bound of my port q -> channel word of the in-lane it feeds
-            int dst, dlane;
-            if (q < P.intra_radix) {
-                int dlid = A.loc_dest[c.lid * P.intra_radix + q];
-                dst = dlid < 0 ? -1 : c.grp * P.a + dlid;
-                dlane = dlid < 0 ? -1 : A.lout_lane[c.lid * P.intra_radix + q];
-            } else {
-                dst = A.gdest[(size_t)c.r * P.h + (q - P.intra_radix)];
-                dlane = dst < 0 ? -1 : A.gout_lane[(size_t)c.r * P.h + (q - P.intra_radix)];
-            }
-            if (dst >= 0) {
-                const PortState& ps = c.port[q];
-                double st = ps.in_send_loop ? c.skey[q].ts : c.rclock;
-                double injrd = q < P.intra_radix ? P.lb_injrd_local : P.lb_injrd_global;
-                double delay = q < P.intra_radix ? P.local_delay : P.global_delay;
-                unsigned long long w = cw_pack(lower((maxd(ps.noat, st) + injrd) + delay), c.lane[q].sent_c);
-                if (w != pubc[q]) {
-                    pubc[q] = w;
+        unsigned long long** tgtc = A.tgt_c + (size_t)rl * P.radix;
+        unsigned long long** tgtk = A.tgt_k + (size_t)rl * P.radix;
+        if (first) {  // resolve once where this router's channel words go
+            LANE_FOR(q, P.ext) {
+                int dst, dlane, src, sport;
+                if (q < P.intra_radix) {
+                    int dlid = A.loc_dest[c.lid * P.intra_radix + q];
+                    dst = dlid < 0 ? -1 : c.grp * P.a + dlid;
+                    dlane = dlid < 0 ? -1 : A.lout_lane[c.lid * P.intra_radix + q];
+                    int v = A.lin_src[c.lid * P.intra_radix + q];
+                    src = v < 0 ? -1 : c.grp * P.a + (v >> 16);
+                    sport = v & 0xFFFF;
+                } else {
+                    dst = A.gdest[(size_t)c.r * P.h + (q - P.intra_radix)];
+                    dlane = dst < 0 ? -1 : A.gout_lane[(size_t)c.r * P.h + (q - P.intra_radix)];
+                    src = A.gin_src[(size_t)c.r * P.h + (q - P.intra_radix)];
+                    sport = src < 0 ? -1 : A.gin_port[(size_t)c.r * P.h + (q - P.intra_radix)];
+                }
+                unsigned long long* tc = nullptr;
+                unsigned long long* tk = nullptr;
+                if (dst >= 0) {
                     unsigned dl;
                     int owner = router_home(c, (unsigned)dst, &dl);
-                    unsigned long long* target = A.cw_c + (size_t)dl * P.radix + dlane;
-                    if (owner != X.rank) target = on_rank(X, target, owner);
-                    st_strong64(target, w, owner != X.rank);
+                    tc = A.cw_c + (size_t)dl * P.radix + dlane;
+                    if (owner != X.rank) tc = on_rank(X, tc, owner);
+                }
+                if (src >= 0) {
+                    unsigned ul;
+                    int owner = router_home(c, (unsigned)src, &ul);
+                    tk = A.cw_k + (size_t)ul * P.radix + sport;
+                    if (owner != X.rank) tk = on_rank(X, tk, owner);
+                }
+                tgtc[q] = tc;
+                tgtk[q] = tk;
+            }
+        }
+        LANE_FOR(q, P.ext) {
+            // chunk bound of my port q -> channel word of the in-lane it feeds.  Far ahead of anything the neighbour can
+            // be waiting for (it carries at least router_delay + link delay), so it is re-published only when it announces
+            // new records or has moved by a good part of that lookahead: every store wakes the neighbour up.
+            unsigned long long* tc = tgtc[q];
+            if (tc) {
+                const PortState& ps = c.port[q];
+                const bool loc = q < P.intra_radix;
+                double st = ps.in_send_loop ? c.skey[q].ts : c.rclock;
+                double bound = lower((maxd(ps.noat, st) + (loc ? P.lb_injrd_local : P.lb_injrd_global)) + (loc ? P.local_delay : P.global_delay));
+                unsigned long long w = cw_pack(bound, c.lane[q].sent_c);
+                unsigned long long old = pubc[q];
+                if (w != old && (((w ^ old) & DFD_STAMP_MASK) != 0 || old == ~0ULL || !(bound < cw_bound(old) + (loc ? P.hyst_local : P.hyst_global)))) {
+                    pubc[q] = w;
+                    st_strong64(tc, w, sys);
                 }
             }
             // credit bound of my in-lane q -> channel word of the port that feeds it
-            int src, sport;
-            if (q < P.intra_radix) {
-                int v = A.lin_src[c.lid * P.intra_radix + q];
-                src = v < 0 ? -1 : c.grp * P.a + (v >> 16);
-                sport = v & 0xFFFF;
-            } else {
-                src = A.gin_src[(size_t)c.r * P.h + (q - P.intra_radix)];
-                sport = src < 0 ? -1 : A.gin_port[(size_t)c.r * P.h + (q - P.intra_radix)];
-            }
-            if (src >= 0) {
+            unsigned long long* tk = tgtk[q];
+            if (tk) {
                 const LaneCtl L = c.lane[q];
                 double a_in = L.chead != L.ctail ? c.ckey[q].ts : cw_bound(c.seen_c[q]);
                 double cd = q < P.intra_radix ? P.local_credit : P.global_credit;
                 unsigned long long w = cw_pack(cd + mind(a_in, late_credit_bound(c, q)), L.sent_k);
                 if (w != pubk[q]) {
                     pubk[q] = w;
-                    unsigned ul;
-                    int owner = router_home(c, (unsigned)src, &ul);
-                    unsigned long long* target = A.cw_k + (size_t)ul * P.radix + sport;
-                    if (owner != X.rank) target = on_rank(X, target, owner);
-                    st_strong64(target, w, owner != X.rank);
+                    st_strong64(tk, w, sys);
                 }
             }
         }
     }
+    t1 = CYC_NOW();
+    c.cyc[4] += t1 - t0;
     return res;
 }

@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
     c.A = &A;
     c.X = &X;
     c.ev = s_ev;
+    c.port = nullptr;
+    c.rl = 0xFFFFFFFFu;
+    for (int i = 0; i < 6; i++) c.cyc[i] = 0;
+    c.nrounds = 0;
     const unsigned ngroups = (unsigned)(X.r1 - X.r0);
     const unsigned w = blockIdx.x, nw = gridDim.x;
     unsigned long long n_act = 0, n_prod = 0, n_exec = 0, idle_passes = 0, passes = 0;
@@ -77,6 +81,8 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
     unsigned long long last_consumed = ~0ULL, last_change_ns = globaltimer_ns();
     for (;;) {
         long long c0 = clock64();
+        // run control: requested before the pass so that its latency overlaps the channel-word poll
+        const unsigned long long err = ld_strong64(&A.ctrl->error), done = ld_strong64(&A.ctrl->done);
         unsigned nexec = 0;
         for (unsigned g = w; g < ngroups; g += nw) {
             ActResult a = group_activate(c, g);
@@ -94,8 +100,6 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         }
         n_exec += nexec;
         passes++;
-        // run control: one strong load of (error, done) per pass
-        unsigned long long err = ld_strong64(&A.ctrl->error), done = ld_strong64(&A.ctrl->done);
         if (err | done) break;
         if (w == 0 && nexec == 0 && (idle_passes & 7) == 1) {
             if (monitor_check(A, X, &last_consumed, &last_change_ns, timeout_ns, c)) break;
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         atomicAdd(&A.counters[23], passes);
         atomicMax(&A.counters[24], (unsigned long long)t_busy);
         atomicAdd(&A.counters[25], n_exec);
+        for (int i = 0; i < 5; i++) atomicAdd(&A.counters[30 + i], (unsigned long long)c.cyc[i]);
+        atomicAdd(&A.counters[35], c.nrounds);
     }
 }
 
@@ -235,6 +241,8 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.seen_k, NR * radix)) return 1;
     if (dalloc(dev, &A.pub_c, NR * radix)) return 1;
     if (dalloc(dev, &A.pub_k, NR * radix)) return 1;
+    if (dalloc(dev, &A.tgt_c, NR * radix)) return 1;
+    if (dalloc(dev, &A.tgt_k, NR * radix)) return 1;
     if (dalloc(dev, &A.nq, NR * radix * radix + 16)) return 1;
     if (dalloc(dev, &A.qbits, NR * radix * 2)) return 1;
     if (dalloc(dev, &A.iblk, NR * 2 * P.p)) return 1;

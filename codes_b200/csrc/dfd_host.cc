@@ -965,6 +965,9 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     L = std::min(L, p.global_credit_delay);
     if (!(L > 0)) return fail(e, "this engine needs strictly positive link and credit delays (smallest is %g ns)", L);
     P->min_delay = L;
+    // hysteresis of the chunk bounds: a quarter of the smallest chunk lookahead of the link kind
+    P->hyst_local = 0.25 * (p.router_delay + p.local_delay);
+    P->hyst_global = 0.25 * (p.router_delay + p.global_delay);
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
     P->traffic = o.traffic;
     P->num_msgs = o.num_messages;
@@ -1158,6 +1161,8 @@ static void profile_print(dfd_engine* e) {
         if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu\n", names[i], C[4 + i]);
     fprintf(stderr, "  warps %d, passes %llu, activations past the poll %llu, productive %llu, events/productive activation %.2f\n", e->dev.grid, C[23], C[22], C[1],
             C[1] ? (double)C[0] / C[1] : 0.0);
+    fprintf(stderr, "  rounds %llu; cycles per warp inside activations: poll-tail %.0f, terminal bounds %.0f, router phase %.0f, node phase %.0f, publish %.0f\n", C[35],
+            (double)C[30] / e->dev.grid, (double)C[31] / e->dev.grid, (double)C[32] / e->dev.grid, (double)C[33] / e->dev.grid, (double)C[34] / e->dev.grid);
     fprintf(stderr, "  cycles per warp: busy passes %.0f, idle passes %.0f, busiest warp %.0f\n", (double)C[20] / e->dev.grid, (double)C[21] / e->dev.grid, (double)C[24]);
 }
 

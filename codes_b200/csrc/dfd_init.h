@@ -49,6 +49,7 @@ DFD_FN void init_node(const DfdParams& P, const DfdArrays& A, const DfdPeers& X,
     ev->d = 0.0;
     s->nev = 1;
     s->nev_hwm = 1;
+    s->self_next = ev->ts;
     A.ncin_tail[nl] = 0;
     A.nkin_tail[nl] = 0;
     A.ack_count[nl] = 0;

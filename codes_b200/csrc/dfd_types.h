@@ -242,6 +242,8 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t mq_head, mq_count;  // FIFO of second-stage MN_BASE_NEW_MSG events
     double last_ts;              // key of the last executed event (causality check)
     uint32_t last_src, last_seq;
+    double self_next;            // earliest timestamp among the self-scheduled events (nev list, mq); +inf: none
+    double pad_d;
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)
@@ -257,6 +259,7 @@ struct DfdParams {
     int credit_size;
     double nic_seq_delay, lookahead, codes_cn_delay;
     double min_delay, ts_end;  // smallest cross-LP delay (a credit delay by default); end of the simulation
+    double hyst_local, hyst_global;  // a chunk bound is re-published only after it has moved by this much (or carries new records)
     // host-precomputed values of bytes_to_ns()/reciprocals (same IEEE operations as the device would do)
     double inj_chunk_cn, inj_chunk_local, inj_chunk_global;  // bytes_to_ns(chunk_size, bw)
     double inj_pay_cn, inj_pay_local, inj_pay_global;        // bytes_to_ns(payload_sz % chunk_size, bw)
@@ -328,6 +331,8 @@ struct DfdArrays {
     unsigned long long* seen_k;
     unsigned long long* pub_c;   // [NRl][radix] channel words as last published
     unsigned long long* pub_k;
+    unsigned long long** tgt_c;  // [NRl][radix] where the chunk word of port j goes (neighbour's cw_c slot, possibly on a peer GPU; 0: no link)
+    unsigned long long** tgt_k;  // [NRl][radix] where the credit word of in-lane j goes (neighbour's cw_k slot)
     unsigned char* nq;           // [NRl][radix][radix] overflowed (queued_msgs) chunks by (in-lane, out port)
     unsigned long long* qbits;   // [NRl][radix][2]     bit q of in-lane s: nq[s][q] > 0
     double* iblk;                // [NRl][2][p]         bounds of the terminal lanes (chunks, credits) for the router phase

@@ -11,6 +11,8 @@
 //   DFD_CPUSIM_SEED   scheduler seed (default 1)
 //   DFD_CPUSIM_WORLD  emulate a group-sharded run over N ranks inside one address space (default 1)
 //   DFD_CPUSIM_WARPS  warps per rank (default: one per group)
+//   DFD_CPUSIM_SYNC   1: synchronous rounds -- every group is activated once per round and sees only what was published
+//                     in earlier rounds; the number of rounds is the length of the dependency chain the bounds leave
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -123,6 +125,8 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
         A.seen_k = halloc<unsigned long long>(R, NR * radix);
         A.pub_c = halloc<unsigned long long>(R, NR * radix);
         A.pub_k = halloc<unsigned long long>(R, NR * radix);
+        A.tgt_c = halloc<unsigned long long*>(R, NR * radix);
+        A.tgt_k = halloc<unsigned long long*>(R, NR * radix);
         A.nq = halloc<unsigned char>(R, NR * radix * radix + 16);
         A.qbits = halloc<unsigned long long>(R, NR * radix * 2);
         A.iblk = halloc<double>(R, NR * 2 * P.p);
@@ -247,14 +251,19 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t) {
     // execute nothing, while events are pending is a deadlock.
     unsigned long long barren = 0, barren_limit = 2000000;
     if (const char* ev = getenv("DFD_CPUSIM_BARREN")) barren_limit = strtoull(ev, nullptr, 10);
+    const bool sync_rounds = getenv("DFD_CPUSIM_SYNC") && atoi(getenv("DFD_CPUSIM_SYNC"));
+    std::vector<std::pair<unsigned long long*, unsigned long long>> deferred;
+    unsigned long long rounds = 0;
     for (;;) {
         bool any = false;
         unsigned long long executed = 0;
+        rounds++;
+        if (sync_rounds) dfd_host_deferred_words = &deferred;
         std::vector<int> order(warps.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
         std::shuffle(order.begin(), order.end(), rng);
         // a few random extra activations in front of the sweep: repeated and skewed progress
-        size_t extra = warps.size() ? rng() % (warps.size() + 1) : 0;
+        size_t extra = warps.size() && !sync_rounds ? rng() % (warps.size() + 1) : 0;
         for (size_t i = 0; i < extra; i++) order.insert(order.begin(), (int)(rng() % warps.size()));
         for (int wi : order) {
             Warp& wp = warps[wi];
@@ -279,6 +288,10 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t) {
             for (Rank& Q : g_sim->ranks) err |= Q.A.ctrl->error != 0;
             if (err) goto done;
         }
+        dfd_host_deferred_words = nullptr;
+        for (auto& pw : deferred) *pw.first = pw.second;
+        if (!deferred.empty()) any = true;
+        deferred.clear();
         unsigned long long created = 0, consumed = 0;
         for (Rank& R : g_sim->ranks) {
             created += R.A.ctrl->created;
@@ -293,6 +306,8 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t) {
         }
     }
 done:
+    dfd_host_deferred_words = nullptr;
+    if (getenv("DFD_CPUSIM_VERBOSE")) fprintf(stderr, "cpusim: %llu rounds, %llu activations past the poll, %llu productive\n", rounds, activations, productive);
     for (int k = 0; k < g_sim->world; k++) {
         Rank& R = g_sim->ranks[k];
         for (int t = 0; t < EV_NTYPES; t++) {

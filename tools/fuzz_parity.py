@@ -3,6 +3,8 @@
 
   python tools/fuzz_parity.py ref  [--cases N] [--seed S]   restatement oracle vs oracle/_ref (reference sources)  -- CPU
   python tools/fuzz_parity.py gpu  [--cases N] [--seed S]   CUDA engine vs restatement oracle                      -- GPU box
+  python tools/fuzz_parity.py sim  [--cases N] [--seed S]   the engine's scheduler + handlers on the CPU harness (tests/cpusim,
+                                                            random interleaving, 1-4 emulated ranks) vs restatement oracle  -- CPU
   python -m torch.distributed.run --nproc-per-node G tools/fuzz_parity.py mgpu ...   group-sharded engine over G GPUs vs oracle
 
 Every case compares all lp-io files (and, on the GPU, the hex-float raw statistics) byte for byte.  A case whose
@@ -88,14 +90,17 @@ def write_conf(tmp, radix, conns, routing, params):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["ref", "gpu", "mgpu"])
+    ap.add_argument("mode", choices=["ref", "gpu", "mgpu", "sim"])
     ap.add_argument("--cases", type=int, default=100)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--verbose", action="store_true", help="print every case before it runs")
     args = ap.parse_args()
     rng = random.Random(args.seed)
     oracle_util.load()
-    if args.mode in ("gpu", "mgpu"):
+    if args.mode in ("gpu", "mgpu", "sim"):
         import codes_b200
+    if args.mode == "sim":
+        from tests import cpusim_util
     dist, rank = None, 0
     if args.mode == "mgpu":  # every rank generates the same cases from the same seed; rank 0 checks
         import torch
@@ -107,6 +112,8 @@ def main():
     for i in range(args.cases):
         radix, conns, routing, params, opts = make_case(rng)
         tag = f"case {i}: shape {radix}/{conns} {routing} {params} {opts}"
+        if args.verbose:
+            print(tag, flush=True)
         with tempfile.TemporaryDirectory() as tmp:
             conf = write_conf(tmp, radix, conns, routing, params)
             try:
@@ -153,7 +160,12 @@ def main():
                     bad += 1
             else:
                 try:
-                    s = codes_b200.run_synthetic(conf, lp_io_dir=os.path.join(tmp, "g"), **opts)
+                    if args.mode == "sim":
+                        world = rng.choice([1, 1, 2, 3, 4])
+                        tag += f" [sim seed {i} world {world}]"
+                        s = cpusim_util.run(conf, lp_io_dir=os.path.join(tmp, "g"), seed=i, world=world, warps=rng.choice([None, None, 3]), **opts)
+                    else:
+                        s = codes_b200.run_synthetic(conf, lp_io_dir=os.path.join(tmp, "g"), **opts)
                     g = oracle_util.read_dir(os.path.join(tmp, "g"))
                     gerr = None
                 except codes_b200.EngineError as ex:

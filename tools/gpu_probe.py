@@ -63,6 +63,13 @@ def perf(conf, reps=3, **opts):
     eng.close()
 
 
+def big(radix, conns, routing, traffic, msgs):
+    import subprocess
+    d = tempfile.mkdtemp()
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(radix), str(conns), d, "--name", "big", "--routing", routing], check=True)
+    perf(os.path.join(d, "big.conf"), reps=2, num_messages=msgs, traffic=traffic)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["parity", "perf"]
     rc = 0
@@ -73,4 +80,8 @@ if __name__ == "__main__":
         perf(C1056, num_messages=100)
         perf(C8K, num_messages=20)
         perf(C8K, num_messages=20, traffic=3)
+    if "big" in what:
+        big(64, 2, "minimal", 1, 10)
+        big(64, 2, "prog-adaptive", 3, 10)
+        big(128, 4, "minimal", 1, 5)
     sys.exit(1 if rc else 0)
