@@ -3,20 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one complete simulation of the workload (BASELINE.json configs[1]: dragonfly-dally 1,056
-terminals, a=8 p=4 h=4 g=33, uniform-random traffic, minimal routing, default credit delay): every LP's
-state is re-initialised on the device, then the window kernel runs the event loop to completion.
-  value      committed events / s, device-timed (CUDA events on the launching stream) over the window kernel,
+Workload (BASELINE.json north_star target / configs[3] scale): dragonfly-dally with 131,584 terminals (a=32 routers per
+group, p=16 terminals and h=16 global channels per router, g=257 groups, 2 links between every pair of groups: the
+topology tools/gen_topology.py writes in the reference's binary link-file format), progressive-adaptive (PAR) routing,
+uniform-random traffic, 10 messages of 2,048 B per terminal -- 30.5 M committed events per step.
+A "step" is one complete simulation: every LP's state is re-initialised on the device, then the persistent event-loop
+kernel runs to completion.
+  value      committed events / s, device-timed (CUDA events on the launching stream) over the event-loop kernel,
              LP state and connection tables already resident in HBM
   e2e        the same metric through the C-ABI call sequence of the reference's main() with host buffers:
              table upload (H2D) + device init + event loop + statistics download (D2H) + *_final handlers
+             (N>1: + merge of the ranks' partitions on rank 0)
   roofline   algorithmic bytes (832*sum(N_hop) + 896*N_chunks per run) / kernel time vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  ensemble   (N=1, extra) 32 independent simulations of the workload at once on the GPU: aggregate events / s
-  cpu_baseline  (N=1) the reference's own handler sources compiled against the sequential shim engine (oracle/_ref,
-             kind "reference"), or the restatement oracle when that binary is absent (kind "port"), single thread,
-             on the same workload
+  worst_case (N=1, extra) the same network under the worst-case group permutation (configs[3]'s traffic)
+  cpu_baseline  (N=1) the CPU implementation of the path, single thread, on a bounded sample of the workload (1 message
+             per terminal, 3.1 M events).  At this size that is the restatement oracle (kind "port"): oracle/_ref, the
+             reference's own sources on the sequential shim engine, needs more than 15 minutes to set this network up.
 --impl reference times that CPU implementation alone (the real ROSS + MPI are external and absent here).
+N>1: the dragonfly groups are sharded over the GPUs (one process per GPU); chunks, credits and channel words of the global
+links are written straight into the owner GPU's memory over NVLink (CUDA-IPC), there is no barrier and no collective.
 """
 import argparse
 import json
@@ -24,14 +30,26 @@ import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(conf=os.path.join(ROOT, "configs", "dfdally-1056.conf"), traffic=1, num_messages=100, payload_sz=2048)
-WORKLOAD_NAME = "dragonfly-dally 1,056-terminal (a=8,p=4,h=4,g=33) uniform-random, minimal routing, 100 msgs/terminal x 2048 B, arrival 1000 ns"
+SHAPE = dict(radix=64, conns=2, routing="prog-adaptive")  # a=32 p=16 h=16 g=257 -> 8,224 routers, 131,584 terminals
+WORKLOAD = dict(traffic=1, num_messages=10, payload_sz=2048)
+SAMPLE = dict(traffic=1, num_messages=1, payload_sz=2048)   # bounded sample of the workload for the CPU arm
+WORKLOAD_NAME = ("dragonfly-dally 131,584-terminal (a=32,p=16,h=16,g=257, 2 links per group pair) uniform-random, "
+                 "progressive-adaptive (PAR) routing, 10 msgs/terminal x 2048 B, arrival 1000 ns")
+
+
+def make_network(tmp):
+    """Writes the link files and the .conf of the bench network (same binary formats the reference reads)."""
+    d = os.path.join(tmp, "net")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_topology.py"), str(SHAPE["radix"]), str(SHAPE["conns"]), d,
+                    "--name", "bench", "--routing", SHAPE["routing"]], check=True, stdout=subprocess.DEVNULL)
+    return os.path.join(d, "bench.conf")
 
 
 def peaks():
@@ -81,7 +99,7 @@ class ClockSampler:
 
 def measured_traffic():
     """DRAM bytes per launch of the window kernel for this workload, from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)["dram_bytes_per_launch"]
@@ -92,51 +110,76 @@ def algorithmic_bytes(total_hops, chunks):
     return 832 * total_hops + 896 * chunks
 
 
+def cpu_sample(conf):
+    """One run of the CPU implementation on the bounded sample; returns (events, packets, event-loop seconds, kind)."""
+    from tests import oracle_util
+    r = oracle_util.run(conf, **SAMPLE)
+    return r.events, r.finished_packets, r.run_seconds, "port"
+
+
+CPU_SAMPLE_TEXT = ("1 of the workload's 10 messages per terminal on the same 131,584-terminal network (3.1 M events per run): the "
+                   "restatement oracle (oracle/dfdally_oracle.cpp), single-threaded -- oracle/_ref (the reference's own sources on "
+                   "the sequential shim engine) cannot set a network of this size up within 15 minutes; ROSS+MPI are external and absent")
+
+
 def run_reference(args, rank):
-    """The reference arm: the reference's own CPU implementation of the path on the box's host cores.
-    oracle/_ref = the reference's handler sources compiled unchanged against a sequential ROSS/MPI shim (ROSS itself
-    is external and absent, so this is the reference's model code on a minimal sequential engine: --synch=1 analogue;
-    there is no optimistic/MPI mode to run).  Falls back to the restatement oracle when oracle/_ref is missing."""
+    """The reference arm: the CPU implementation of the path on the box's host cores, one bounded sample per step.
+    The algorithm is sequential (one event list), so it uses one core."""
     if rank != 0:
         return
-    import tempfile
     from tests import oracle_util
-    w = dict(WORKLOAD)
-    conf = w.pop("conf")
-    use_ref = oracle_util.ref_available()
+    oracle_util.load()
     events = packets = 0
     loop = 0.0
     t0 = time.perf_counter()
     with tempfile.TemporaryDirectory() as tmp:
-        def once():
-            if use_ref:
-                ev, secs, _ = oracle_util.run_ref(conf, os.path.join(tmp, "lpio"), **w)
-                return ev, 1056 * w["num_messages"], secs
-            r = oracle_util.run(conf, **w)
-            return r.events, r.finished_packets, r.run_seconds
-        if not use_ref:
-            oracle_util.load()
+        conf = make_network(tmp)
         for _ in range(args.warmup):
-            once()
+            cpu_sample(conf)
         for _ in range(args.steps):
-            ev, pk, secs = once()
+            ev, pk, secs, kind = cpu_sample(conf)
             events += ev
             packets += pk
             loop += secs
     wall = time.perf_counter() - t0
     value = events / loop
-    kind = "reference" if use_ref else "port"
-    sample = ("the full workload, %d run(s) of oracle/_ref (the reference's own dragonfly-dally / model-net / synthetic-driver sources, "
-              "unchanged, on a single-threaded sequential shim engine; ROSS+MPI are external and absent)" % args.steps) if use_ref else \
-             ("the full workload, %d run(s) of the restatement oracle (single-threaded)" % args.steps)
     line = {"metric": "committed events/sec", "value": value, "unit": "events/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * loop / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "packets_per_s": packets / loop,
                        "note": "event loop only (config parsing / table construction excluded); wall incl. setup %.3f s" % wall},
-            "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "events/s", "cores": 1, "kind": kind,
+                             "sample": "each step: " + CPU_SAMPLE_TEXT},
             "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def device_timed(eng, stream, flush, fence, sharded, steps, warmup):
+    """W untimed + K timed runs of the event-loop kernel; returns the summed kernel time in ms (this rank)."""
+    import torch
+
+    def one_step(timed):
+        if sharded:
+            fence()  # nobody may re-initialise its exchange region while a peer's kernel is still running
+        eng.reset(stream)
+        flush.fill_(1)  # evict LP state from L2 between steps
+        if sharded:
+            fence()
+        if timed:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.run(stream)
+            e1.record()
+            return e0, e1
+        eng.run(stream)
+        return None
+
+    for _ in range(max(warmup, 0)):
+        one_step(False)
+    fence()
+    evs = [one_step(True) for _ in range(steps)]
+    fence()
+    return sum(a.elapsed_time(b) for a, b in evs)
 
 
 def main():
@@ -146,7 +189,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ensemble", action="store_true", help="skip the 32-simulation ensemble figure (N=1 only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the worst-case-permutation figure (N=1 only)")
     ap.add_argument("--replicas", action="store_true", help="N>1: run N independent replicas instead of the group-sharded engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -167,55 +210,34 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("cpu:gloo,cuda:nccl")
 
+    tmpdir = tempfile.TemporaryDirectory()
+    conf = make_network(tmpdir.name)  # every rank writes its own copy (deterministic, 1 MB)
     w = dict(WORKLOAD)
-    conf = w.pop("conf")
     opts = codes_b200.make_opts(**w)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     sharded = world > 1 and not args.replicas
-
-    eng = codes_b200.Engine()
-    eng.setup(conf, opts)
-    if sharded:  # group-sharded over the ranks: P2P inbox writes + cross-GPU window barrier over NVLink
-        eng.set_partition(rank, world)
-    eng.upload(stream)
-    if sharded:
-        handles = [None] * world
-        dist.all_gather_object(handles, eng.ipc_export())
-        eng.ipc_import(handles)
 
     def fence():
         torch.cuda.synchronize()
         if dist:
             dist.barrier()
 
-    def one_step(timed):
-        if sharded:
-            fence()  # nobody may reset its sync block while a peer is still closing the last window
-        eng.reset(stream)
-        flush.fill_(1)  # evict LP state from L2 between steps
-        if sharded:
-            fence()
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            eng.run(stream)
-            e1.record()
-            return e0, e1
-        eng.run(stream)
-        return None
-
-    for _ in range(max(args.warmup, 0)):
-        one_step(False)
+    eng = codes_b200.Engine()
+    eng.setup(conf, opts)
+    if sharded:
+        eng.set_partition(rank, world)
+    eng.upload(stream)
+    if sharded:
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export())
+        eng.ipc_import(handles)
     fence()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
+    device_timed(eng, stream, flush, fence, sharded, 0, args.warmup)  # W untimed warm-up steps
     sampler.start()
-    evs = [one_step(True) for _ in range(args.steps)]
-    fence()
-    torch.cuda.synchronize()
+    kernel_ms = device_timed(eng, stream, flush, fence, sharded, args.steps, 0)
     clocks = sampler.stop()
-    kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
     eng.finish(stream)
     if sharded:
         parts = [None] * world
@@ -225,40 +247,45 @@ def main():
                 eng.import_partition(parts[k])
             eng.finalize()
     s = eng.summary()
-    meta = [s.events, s.finished_packets, s.total_hops, s.finished_chunks, s.windows] if rank == 0 or not sharded else [0] * 5
+    meta = [s.events, s.finished_packets, s.total_hops, s.finished_chunks, s.activations] if rank == 0 or not sharded else [0] * 5
     if sharded:
         mt = torch.tensor(meta, dtype=torch.int64, device="cuda")
         dist.broadcast(mt, 0)
         meta = [int(x) for x in mt]
-    events_per_step, packets_per_step, hops, chunks, windows = meta
+    events_per_step, packets_per_step, hops, chunks, activations = meta
 
-    # e2e: the reference's main() call sequence, host buffers on both sides, H2D + D2H inside the timed region
+    # e2e: the reference's main() call sequence on an engine whose configuration is loaded: host buffers on both sides,
+    # H2D of the connection tables + device init + event loop + D2H of the statistics + *_final inside the timed region
     if sharded:
-        codes_b200.run_sharded(conf, dist, stream=stream, **w)  # warm
+        codes_b200.sharded_tw_run(eng, dist, stream)  # warm
         fence()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            es = codes_b200.run_sharded(conf, dist, stream=stream, **w)
+            codes_b200.sharded_tw_run(eng, dist, stream)
         fence()
         e2e_s = time.perf_counter() - t0
-        h2d, d2h = (es.h2d_bytes, es.d2h_bytes) if rank == 0 else (0, 0)
+        es = eng.summary()
+        h2d, d2h = es.h2d_bytes, es.d2h_bytes
+        if rank == 0:
+            assert es.events == events_per_step, (es.events, events_per_step)
     else:
-        e2e_eng = codes_b200.Engine()
-        e2e_eng.setup(conf, opts)
-        e2e_eng.tw_run(stream)  # warm (allocations, module load)
+        eng.tw_run(stream)  # warm
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_eng.tw_run(stream)
+            eng.tw_run(stream)
         e2e_s = time.perf_counter() - t0
-        es = e2e_eng.summary()
+        es = eng.summary()
         assert es.events == events_per_step
         h2d, d2h = es.h2d_bytes, es.d2h_bytes
 
     t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
+    io = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(io, op=dist.ReduceOp.SUM)  # every rank uploads the tables and downloads its own partition
     kernel_ms, e2e_s = float(t[0]), float(t[1])
+    h2d, d2h = int(io[0]), int(io[1])
     jobs = 1 if (sharded or world == 1) else world  # replicas: N independent simulations
     total_events = events_per_step * args.steps * jobs
     value = total_events / (kernel_ms * 1e-3)
@@ -267,85 +294,52 @@ def main():
     if world == 1:
         par = "1 GPU"
     elif sharded:
-        par = f"dragonfly groups sharded over {world} GPUs (one process per GPU): global-link chunks/credits and ACK statistics are " \
-              f"written into the owner GPU's inbox over NVLink P2P, one flag+minimum exchange per lookahead window"
+        par = (f"dragonfly groups sharded over {world} GPUs (one process per GPU, {s.num_routers // world} routers each): chunks, credits and "
+               f"channel words of the global links and the ACK statistics are written into the owner GPU's memory over NVLink P2P "
+               f"(CUDA-IPC); no barrier, no collective on the data path")
     else:
         par = f"{world} independent replicas"
     line = {"metric": "committed events/sec", "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if sharded else "weak",
+            "scaling": "weak" if jobs > 1 else "strong",
             "vs_baseline": None, "dtype": "f64+int32", "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "events_per_step": events_per_step, "packets_per_step": packets_per_step,
                        "packets_per_s": packets_per_step * args.steps * jobs / (kernel_ms * 1e-3),
-                       "windows_per_step": windows, "window_ns": s.window_ns, "us_per_window": 1e3 * kernel_ms / args.steps / max(windows, 1),
-                       "l2": "256 MiB buffer written between timed steps (L2 flush)",
+                       "activations_per_step": activations,
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); LP state of this network is 3.4 GB",
                        "grid": [s.grid_blocks, s.block_threads], "device_bytes": s.device_bytes, "parallelism": par},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * (world if sharded or jobs > 1 else 1), "unit": "GB/s",
-                         "frac": ach / (peak * (world if sharded or jobs > 1 else 1)), "traffic": measured_traffic() if world == 1 else None,
-                         "algorithmic_bytes_per_launch": algorithmic_bytes(hops, chunks),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak * world, "unit": "GB/s",
+                         "frac": ach / (peak * world), "traffic": measured_traffic() if world == 1 else None,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(hops, chunks) // (world if sharded else 1),
                          "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step per GPU)",
-                         "note": "the kernel is bound by per-window latency (grid barrier + dependent instruction chain of the slowest LP), not by HBM bandwidth; see DESIGN.md 5"},
+                         "note": "memory-latency-bound: one warp per router group walks dependent loads of LP state (DESIGN.md 5)"},
             "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": 2 * args.steps, "clocks": clocks}
-    if world == 1 and not args.no_ensemble:
-        try:
-            # Not the headline: the same workload as a parameter sweep -- 32 independent simulations at once on this GPU,
-            # one engine and CUDA stream each (codes_b200.run_ensemble), device-timed from the first launch to the last finish
-            k = 32
-            engs, streams = [], [torch.cuda.Stream() for _ in range(k)]
-            for st in streams:
-                e = codes_b200.Engine()
-                e.setup(conf, opts)
-                e.set_ensemble(k)
-                e.upload(st.cuda_stream)
-                engs.append(e)
-            torch.cuda.synchronize()
-            for rep in range(2):  # first pass warms up
-                for e, st in zip(engs, streams):
-                    e.reset(st.cuda_stream)
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for e, st in zip(engs, streams):
-                    st.wait_event(e0)
-                    e.run(st.cuda_stream)
-                for st in streams:
-                    torch.cuda.current_stream().wait_stream(st)
-                e1.record()
-                torch.cuda.synchronize()
-                ens_ms = e0.elapsed_time(e1)
-            ens_events = 0
-            for e, st in zip(engs, streams):
-                e.finish(st.cuda_stream)
-                ens_events += e.summary().events
-                e.close()
-            assert ens_events == k * events_per_step
-            line["ensemble"] = {"simulations": k, "value": ens_events / (ens_ms * 1e-3), "unit": "events/s", "ms": ens_ms,
-                                "note": "aggregate of 32 independent simulations of the same workload running concurrently on the one GPU "
-                                        "(a parameter sweep); `value` above is a single simulation"}
+            "gpu_launches": 2 * args.steps * world, "clocks": clocks}
+    if world == 1 and not args.no_extras:
+        try:  # not the headline: the same network under the worst-case group permutation (BASELINE configs[3]'s traffic)
+            e2 = codes_b200.Engine()
+            e2.setup(conf, codes_b200.make_opts(**dict(w, traffic=3)))
+            e2.upload(stream)
+            ms = device_timed(e2, stream, flush, fence, False, 3, 1)
+            e2.finish(stream)
+            s2 = e2.summary()
+            e2.close()
+            line["worst_case"] = {"workload": "same network and routing, nearest-group (worst-case group permutation) traffic",
+                                  "value": 3 * s2.events / (ms * 1e-3), "unit": "events/s", "events_per_step": s2.events, "steps": 3}
         except Exception as ex:  # the extra figure must never cost the headline
-            line["ensemble"] = {"error": repr(ex)[:200]}
+            line["worst_case"] = {"error": repr(ex)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is timed at N=1 only
-        import tempfile
-        from tests import oracle_util
-        if oracle_util.ref_available():
-            with tempfile.TemporaryDirectory() as tmp:
-                ev, secs, _ = oracle_util.run_ref(conf, os.path.join(tmp, "lpio"), **w)
-            assert ev == events_per_step, (ev, events_per_step)
-            line["cpu_baseline"] = {"value": ev / secs, "unit": "events/s", "cores": 1, "kind": "reference",
-                                    "sample": "the full workload once (%d events, %.2f s event loop): oracle/_ref = the reference's own handler "
-                                              "sources on a single-threaded sequential shim engine (ROSS+MPI are external and absent)" % (ev, secs)}
-        else:
-            oracle_util.load()
-            r = oracle_util.run(conf, **w)
-            assert r.events == events_per_step, (r.events, events_per_step)
-            line["cpu_baseline"] = {"value": r.events / r.run_seconds, "unit": "events/s", "cores": 1, "kind": "port",
-                                    "sample": "the full workload once (%d events, %.2f s): restatement oracle, single-threaded" % (r.events, r.run_seconds)}
+        ev, pk, secs, kind = cpu_sample(conf)
+        line["cpu_baseline"] = {"value": ev / secs, "unit": "events/s", "cores": 1, "kind": kind,
+                                "sample": "one run (%d events, %.2f s event loop): " % (ev, secs) + CPU_SAMPLE_TEXT}
     if rank == 0:
         print(json.dumps(line))
+    eng.close()
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
+    tmpdir.cleanup()
 
 
 if __name__ == "__main__":

@@ -95,6 +95,7 @@ ABI = [
     ("dfd_engine_set_partition", _I, [_P, _I, _I]),
     ("dfd_engine_ipc_export", _I, [_P, _P]),
     ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
+    ("dfd_engine_ipc_ready", _I, [_P]),
     ("dfd_engine_partition_bytes", _LL, [_P]),
     ("dfd_partition_bounds", _I, [_I, _I, _I, _I, _I, ctypes.POINTER(_I)]),
     ("dfd_engine_export_partition", _I, [_P, _P, _LL]),
@@ -268,6 +269,9 @@ class Engine:
         blob = b"".join(handles)
         self._ck(self._lib.dfd_engine_ipc_import(self._h, blob, len(handles)))
 
+    def ipc_ready(self):
+        return bool(self._lib.dfd_engine_ipc_ready(self._h))
+
     def export_partition(self):
         n = self._lib.dfd_engine_partition_bytes(self._h)
         buf = ctypes.create_string_buffer(n)
@@ -337,32 +341,62 @@ def run_ensemble(conf_path, variants, lp_io_dirs=None, streams=None):
             e.close()
 
 
+def sharded_tw_run(eng, dist, stream=None):
+    """tw_run() of a group-sharded engine (set_partition done): upload, exchange of the CUDA-IPC handles when the device
+    arrays are new, event loop, download, merge of the partitions on rank 0.  Collective over `dist`; a failure on any
+    rank is raised on every rank instead of leaving the others blocked in the gather."""
+    import torch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    err = None
+    try:
+        eng.upload(stream)
+    except EngineError as ex:
+        err = ex
+    ready = [None] * world
+    dist.all_gather_object(ready, (err is None, err is None and eng.ipc_ready()))
+    if not all(r[0] for r in ready):
+        raise err or EngineError("group-sharded run: another rank failed in engine_upload")
+    if not all(r[1] for r in ready):
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export())
+        if not eng.ipc_ready():
+            eng.ipc_import(handles)
+    torch.cuda.synchronize()
+    dist.barrier()  # every rank's state is initialised before any kernel starts writing to its neighbours
+    try:
+        eng.run(stream)
+        eng.finish(stream)
+        blob = eng.export_partition()
+    except EngineError as ex:
+        err, blob = ex, None
+    oks = [None] * world
+    dist.all_gather_object(oks, err is None)
+    if not all(oks):
+        raise err or EngineError("group-sharded run: another rank reported a device error")
+    parts = [None] * world
+    dist.gather_object(blob if rank != 0 else None, parts if rank == 0 else None, dst=0)
+    if rank == 0:
+        for k in range(1, world):
+            eng.import_partition(parts[k])
+        eng.finalize()
+    dist.barrier()
+
+
 def run_sharded(conf_path, dist, lp_io_dir=None, stream=None, **opts):
     """Group-sharded run over the ranks of an initialised torch.distributed process group (one GPU per rank).
     Every rank simulates its own dragonfly groups; rank 0 returns the merged Summary (other ranks return None)."""
     rank, world = dist.get_rank(), dist.get_world_size()
     eng = Engine()
-    eng.setup(conf_path, make_opts(**opts))
-    eng.set_partition(rank, world)
-    eng.upload(stream)
-    handles = [None] * world
-    dist.all_gather_object(handles, eng.ipc_export())
-    eng.ipc_import(handles)
-    import torch
-    torch.cuda.synchronize()
-    dist.barrier()
-    eng.run(stream)
-    eng.finish(stream)
-    parts = [None] * world
-    dist.gather_object(eng.export_partition(), parts if rank == 0 else None, dst=0)
-    out = None
-    if rank == 0:
-        for k in range(1, world):
-            eng.import_partition(parts[k])
-        eng.finalize()
-        if lp_io_dir:
-            eng.lp_io_flush(lp_io_dir)
-        out = eng.summary()
-    dist.barrier()
-    eng.close()
-    return out
+    try:
+        eng.setup(conf_path, make_opts(**opts))
+        eng.set_partition(rank, world)
+        sharded_tw_run(eng, dist, stream)
+        out = None
+        if rank == 0:
+            if lp_io_dir:
+                eng.lp_io_flush(lp_io_dir)
+            out = eng.summary()
+        dist.barrier()
+        return out
+    finally:
+        eng.close()

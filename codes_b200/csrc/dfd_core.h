@@ -34,6 +34,7 @@
 #ifdef __CUDACC__
 #define DFD_FN __device__ __forceinline__
 #define DFD_FN_NOINLINE __device__
+#define DFD_FN_OUTLINE __device__ __noinline__  // shared or cold code: one copy instead of one per call site (instruction cache)
 #define DFD_LANE() ((int)(threadIdx.x & 31u))
 #define LANE_FOR(i, n) for (int i = DFD_LANE(); i < (int)(n); i += 32)
 #define IS_LANE0() (DFD_LANE() == 0)
@@ -99,6 +100,7 @@ DFD_FN int warp_sum_i(int v) {
 #include <math.h>
 #define DFD_FN static inline
 #define DFD_FN_NOINLINE static
+#define DFD_FN_OUTLINE static
 #define DFD_LANE() 0
 #define LANE_FOR(i, n) for (int i = 0; i < (int)(n); i++)
 #define IS_LANE0() true
@@ -266,53 +268,79 @@ struct Ctx {
 #define CYC_NOW() 0LL
 #endif
 
-DFD_FN void set_error(const Ctx& c, unsigned code, unsigned long long info) {
-    const DfdArrays& A = *c.A;
-    if (cas_u64(&A.ctrl->error, 0ULL, (unsigned long long)code)) A.ctrl->error_info = info;
+// First error wins.  Outlined (cold, dozens of call sites) and given only a global pointer, so that no kernel-parameter
+// struct has to be materialised in local memory for it.  Peers learn about the error from this rank's monitor path
+// (propagate_error), which every warp runs when it leaves the event loop.
+DFD_FN_OUTLINE void set_error_at(DfdCtrl* ctrl, unsigned code, unsigned long long info) {
+    if (cas_u64(&ctrl->error, 0ULL, (unsigned long long)code)) ctrl->error_info = info;
+}
+DFD_FN void set_error(const Ctx& c, unsigned code, unsigned long long info) { set_error_at(c.A->ctrl, code, info); }
+DFD_FN void propagate_error(const DfdArrays& A, const DfdPeers& X) {
 #ifdef __CUDACC__
-    const DfdPeers& X = *c.X;
     for (int k = 0; k < X.world; k++)
         if (k != X.rank) {
             DfdCtrl* pc = (DfdCtrl*)(X.base[k] + ((char*)A.ctrl - X.local_base));
             atomicCAS_system(&pc->error, 0ULL, (unsigned long long)DFD_ERR_PEER_ERROR);
         }
+#else
+    (void)A;
+    (void)X;
 #endif
 }
 
 // ------------------------------------------------------------------------------------------------
 // CLCG4 (L'Ecuyer-Andres), int32 Schrage form; identical values to ROSS' rng_gen_val
 // ------------------------------------------------------------------------------------------------
-DFD_FN double clcg4_unif(int32_t* s) {
+struct Clcg4Step {
+    int32_t s0, s1, s2, s3;
+    double u;
+};
+// one step of the four component generators; by value in and out so that the caller's state stays in registers
+DFD_FN_OUTLINE Clcg4Step clcg4_step(int32_t s0, int32_t s1, int32_t s2, int32_t s3) {
     int k, v;
     double u = 0.0;
-    v = s[0];
+    v = s0;
     k = v / 46693;
     v = 45991 * (v - k * 46693) - k * 25884;
     if (v < 0) v = v + 2147483647;
-    s[0] = v;
+    s0 = v;
     u = u + 4.65661287524579692e-10 * v;
-    v = s[1];
+    v = s1;
     k = v / 10339;
     v = 207707 * (v - k * 10339) - k * 870;
     if (v < 0) v = v + 2147483543;
-    s[1] = v;
+    s1 = v;
     u = u - 4.65661310075985993e-10 * v;
     if (u < 0) u = u + 1.0;
-    v = s[2];
+    v = s2;
     k = v / 15499;
     v = 138556 * (v - k * 15499) - k * 3979;
     if (v < 0) v = v + 2147483423;
-    s[2] = v;
+    s2 = v;
     u = u + 4.65661336096842131e-10 * v;
     if (u >= 1.0) u = u - 1.0;
-    v = s[3];
+    v = s3;
     k = v / 43218;
     v = 49689 * (v - k * 43218) - k * 24121;
     if (v < 0) v = v + 2147483323;
-    s[3] = v;
+    s3 = v;
     u = u - 4.65661357780891134e-10 * v;
     if (u < 0) u = u + 1.0;
-    return u;
+    Clcg4Step o;
+    o.s0 = s0;
+    o.s1 = s1;
+    o.s2 = s2;
+    o.s3 = s3;
+    o.u = u;
+    return o;
+}
+DFD_FN double clcg4_unif(int32_t* s) {
+    Clcg4Step o = clcg4_step(s[0], s[1], s[2], s[3]);
+    s[0] = o.s0;
+    s[1] = o.s1;
+    s[2] = o.s2;
+    s[3] = o.s3;
+    return o.u;
 }
 // tw_rand_integer: low + (long)(unif * (high + 1 - low)); no draw when high < low
 DFD_FN long long clcg4_integer(int32_t* s, long long low, long long high, unsigned long long* draws) {
@@ -1854,9 +1882,6 @@ struct ActResult {
     bool polled_change;
 };
 
-#ifndef DFD_ACT_BUDGET
-#define DFD_ACT_BUDGET 4  // router events after which an activation publishes its bounds even if more would be safe
-#endif
 
 // earliest pending event of a terminal: self events and the heads of its two rings
 DFD_FN double node_next_pending(const Ctx& c, unsigned nl, const NodeState* ns) {
@@ -1975,7 +2000,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
         t1 = CYC_NOW();
         c.cyc[1] += t1 - t0;
         t0 = t1;
-        unsigned nr = router_phase(c, &hd, DFD_ACT_BUDGET - nrouter);
+        unsigned nr = router_phase(c, &hd, (unsigned)P.act_budget - nrouter);
         nrouter += nr;
         WARP_SYNC();
         t1 = CYC_NOW();
@@ -2007,7 +2032,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
         }
 #endif
         if ((nr + nn) == 0 && (!(c.rclock > clock_in) || c.nothing_pending)) break;  // fixed point
-        if (nrouter >= DFD_ACT_BUDGET) {  // publish what is known so far; the next pass continues
+        if (nrouter >= (unsigned)P.act_budget) {  // publish what is known so far; the next pass continues
             more = true;
             break;
         }

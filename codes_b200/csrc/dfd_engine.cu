@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         }
         n_exec += nexec;
         passes++;
-        if (err | done) break;
+        if (err | done) {
+            if (err && w == 0 && lane == 0 && X.world > 1) propagate_error(A, X);
+            break;
+        }
         if (w == 0 && nexec == 0 && (idle_passes & 7) == 1) {
             if (monitor_check(A, X, &last_consumed, &last_change_ns, timeout_ns, c)) break;
         }
@@ -300,6 +303,10 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     bool wide = groups <= (size_t)dev->num_sms * 8 && ensemble <= 1;
     if (const char* ev = getenv("DFD_WIDE_REGS")) wide = atoi(ev) != 0;
     dev->kernel = wide ? (const void*)dfd_run_kernel<8> : (const void*)dfd_run_kernel<16>;
+    if (const char* ev = getenv("DFD_MINBLOCKS")) {
+        int mb = atoi(ev);
+        dev->kernel = mb == 8 ? (const void*)dfd_run_kernel<8> : mb == 32 ? (const void*)dfd_run_kernel<32> : (const void*)dfd_run_kernel<16>;
+    }
     dev->smem = 0;
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (void (*)(DfdParams, DfdArrays, DfdPeers, unsigned long long))dev->kernel, dev->block, dev->smem));
@@ -312,6 +319,10 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (ensemble > 1) slots_total = std::max<size_t>(1, slots_total / ensemble);  // the GPU is shared by `ensemble` engines
     dev->grid = (int)std::max<size_t>(1, std::min(groups, slots_total));
     if (const char* ev = getenv("DFD_GRID")) dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
+    // Event budget of one activation.  With a warp per group the run is bound by the chain of dependent activations:
+    // publishing early lets the neighbours start.  With several groups per warp it is bound by throughput: the fixed
+    // cost of an activation (poll, bounds, publish) is spread over more events.
+    if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->grid ? 16 : 4;
     return 0;
 }
 

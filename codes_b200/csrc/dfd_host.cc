@@ -194,6 +194,7 @@ struct dfd_engine {
     DfdHostResults res;
     dfd_summary sum;
     std::vector<LpioFile> lpio;
+    bool lpio_rendered = false;  // the lp-io text records are rendered on demand (render_lpio)
     std::string raw;
     unsigned long long h2d_bytes = 0;
 };
@@ -517,68 +518,103 @@ double bits_to_double(unsigned long long b) {
     return d;
 }
 
-// The *_final handlers in gid order: svr_finalize synthetic:523-577, dragonfly_dally_terminal_final
-// dally:6791-6862 (+ model_net_print_stats model-net.c:186-226), dragonfly_dally_router_final dally:6974-7041
+// The *_final handlers: svr_finalize synthetic:523-577, dragonfly_dally_terminal_final dally:6791-6862 (+ model_net_print_stats
+// model-net.c:186-226), dragonfly_dally_router_final dally:6974-7041.  They do two things in the reference: fold the LP's
+// counters into the run totals and lp_io_write() a text record.  Here the totals are folded when the run finishes
+// (finalize, part of tw_run) and the text records are rendered when lp_io_flush asks for them (render_lpio): a caller
+// that only reads the summary never pays for 1.2 M snprintf calls on a 131,584-terminal network.
+struct SvrLoad {
+    double first_recv_ts, last_recv_ts, observed_load, observed_load_time, offered_load;
+};
+static SvrLoad svr_load(const dfd_engine* e, unsigned k) {  // synthetic:533-560
+    const dfd_synthetic_opts& o = e->opts;
+    const unsigned long long INF = 0x7FF0000000000000ULL;
+    const NodeState& ns = e->res.node[k];
+    SvrLoad L;
+    L.first_recv_ts = e->res.ack_first[k] == INF ? -1.0 : bits_to_double(e->res.ack_first[k]);
+    L.last_recv_ts = bits_to_double(e->res.ack_last[k]);
+    double start_ts = e->mean_interval;
+    L.observed_load_time = ((double)L.last_recv_ts - o.warm_up_time) - L.first_recv_ts;
+    double observed_load = ((double)o.payload_sz * (double)ns.msg_recvd_count) / L.observed_load_time;
+    observed_load = observed_load * (double)(1000 * 1000 * 1000);
+    L.observed_load = observed_load / (double)(1024 * 1024 * 1024);
+    double offered_load_time = ((double)ns.last_send_ts - o.warm_up_time) - start_ts;
+    double offered_load = ((double)o.payload_sz * (double)ns.warm_msg_sent_count) / offered_load_time;
+    offered_load = offered_load * (double)(1000 * 1000 * 1000);
+    L.offered_load = offered_load / (double)(1024 * 1024 * 1024);
+    return L;
+}
+
 void finalize(dfd_engine* e) {
     const HostParams& p = e->hp;
-    const dfd_synthetic_opts& o = e->opts;
     dfd_summary& S = e->sum;
     e->lpio.clear();
+    e->lpio_rendered = false;
     e->raw.clear();  // built on demand (build_raw)
     const unsigned long long* C = e->res.counters;
     S.events = C[0];
     S.windows = C[1];
     for (int i = 0; i < EV_NTYPES && i < 16; i++) S.events_by_type[i] = C[4 + i];
-    const unsigned long long INF = 0x7FF0000000000000ULL;
+    // the same accumulation order as the reference's final handlers (gid order: floating-point sums depend on it)
+    for (int rep = 0; rep < p.repetitions; rep++) {
+        for (int i = 0; i < p.n_svr; i++) {
+            unsigned k = rep * p.n_svr + i;
+            const NodeState& ns = e->res.node[k];
+            SvrLoad L = svr_load(e, k);
+            if (L.last_recv_ts > S.max_end_ts) S.max_end_ts = L.last_recv_ts;  // pe_max_end_ts synthetic:427-430
+            S.svr_sum_latency += ns.sum_server_latency;
+            S.svr_msgs_recvd += ns.msg_recvd_count;
+            if (ns.max_server_latency > S.svr_max_latency) S.svr_max_latency = ns.max_server_latency;
+            S.total_offered_load += L.offered_load;
+            S.total_observed_load += L.observed_load;
+        }
+        for (int i = 0; i < p.n_term; i++) {
+            unsigned k = rep * p.n_term + i;
+            const NodeState& s = e->res.node[k];
+            S.total_time += s.total_time;
+            if (s.max_latency > S.max_latency) S.max_latency = s.max_latency;
+            S.total_hops += (long long)s.total_hops;
+            S.finished_packets += s.finished_packets;
+            S.finished_msgs += s.finished_msgs;
+            S.finished_chunks += s.finished_chunks;
+            S.total_msg_sz += (long long)s.total_msg_size;
+            S.packet_gen += s.packet_gen;
+            S.packet_fin += s.packet_fin;
+            S.local_same_router += s.local_sr;
+            S.local_same_group += s.local_sg;
+            S.remote += s.remote_pk;
+            S.minimal_count += s.minimal_count;
+            S.nonmin_count += s.nonmin_count;
+            S.rng_draws += s.rng_draws;
+        }
+        S.rng_draws += e->res.rh[rep].rng_draws;
+    }
+}
+
+// the lp-io text records of the final handlers, in gid order
+void render_lpio(dfd_engine* e) {
+    if (e->lpio_rendered) return;
+    const HostParams& p = e->hp;
+    const dfd_synthetic_opts& o = e->opts;
+    e->lpio.clear();
     for (int rep = 0; rep < p.repetitions; rep++) {
         for (int off = 0; off < p.lps_per_rep; off++) {
             unsigned g = (unsigned)rep * p.lps_per_rep + off;
             if (off >= p.off_svr && off < p.off_svr + p.n_svr) {
                 unsigned k = rep * p.n_svr + (off - p.off_svr);
                 const NodeState& ns = e->res.node[k];
-                double first_recv_ts = e->res.ack_first[k] == INF ? -1.0 : bits_to_double(e->res.ack_first[k]);
-                double last_recv_ts = bits_to_double(e->res.ack_last[k]);
-                if (last_recv_ts > S.max_end_ts) S.max_end_ts = last_recv_ts;  // pe_max_end_ts synthetic:427-430
-                S.svr_sum_latency += ns.sum_server_latency;
-                S.svr_msgs_recvd += ns.msg_recvd_count;
-                if (ns.max_server_latency > S.svr_max_latency) S.svr_max_latency = ns.max_server_latency;
-                double start_ts = e->mean_interval;
-                double observed_load_time = ((double)last_recv_ts - o.warm_up_time) - first_recv_ts;
-                double observed_load = ((double)o.payload_sz * (double)ns.msg_recvd_count) / observed_load_time;
-                observed_load = observed_load * (double)(1000 * 1000 * 1000);
-                observed_load = observed_load / (double)(1024 * 1024 * 1024);
-                double offered_load_time = ((double)ns.last_send_ts - o.warm_up_time) - start_ts;
-                double offered_load = ((double)o.payload_sz * (double)ns.warm_msg_sent_count) / offered_load_time;
-                offered_load = offered_load * (double)(1000 * 1000 * 1000);
-                offered_load = offered_load / (double)(1024 * 1024 * 1024);
-                S.total_offered_load += offered_load;
-                S.total_observed_load += observed_load;
+                SvrLoad L = svr_load(e, k);
                 std::string rec;
                 if (g == 0)
                     rec += "# Format <LP id> <Msgs Sent> <Msgs Recvd> <Bytes Sent> <Bytes Recvd> <Offered Load [GBps]> <Observed Load [GBps]> <End Time [ns]>\n";
                 rec += sfmt("%llu %d %d %d %d %f %f %f %f\n", (unsigned long long)g, ns.msg_sent_count, ns.msg_recvd_count,
-                            o.payload_sz * ns.msg_sent_count, o.payload_sz * ns.msg_recvd_count, e->load * p.svr_link_bandwidth, observed_load,
-                            last_recv_ts, observed_load_time);
+                            o.payload_sz * ns.msg_sent_count, o.payload_sz * ns.msg_recvd_count, e->load * p.svr_link_bandwidth, L.observed_load,
+                            L.last_recv_ts, L.observed_load_time);
                 lpio_write(e, "synthetic-stats", rec);
             } else if (off >= p.off_term && off < p.off_term + p.n_term) {
                 unsigned k = rep * p.n_term + (off - p.off_term);
                 const NodeState& s = e->res.node[k];
                 unsigned router_id = k / p.num_cn;
-                S.total_time += s.total_time;
-                if (s.max_latency > S.max_latency) S.max_latency = s.max_latency;
-                S.total_hops += (long long)s.total_hops;
-                S.finished_packets += s.finished_packets;
-                S.finished_msgs += s.finished_msgs;
-                S.finished_chunks += s.finished_chunks;
-                S.total_msg_sz += (long long)s.total_msg_size;
-                S.packet_gen += s.packet_gen;
-                S.packet_fin += s.packet_fin;
-                S.local_same_router += s.local_sr;
-                S.local_same_group += s.local_sg;
-                S.remote += s.remote_pk;
-                S.minimal_count += s.minimal_count;
-                S.nonmin_count += s.nonmin_count;
-                S.rng_draws += s.rng_draws;
                 const char* line = "lp:%ld\tsend_count:%ld\tsend_bytes:%ld\tsend_time:%f\trecv_count:%ld\trecv_bytes:%ld\trecv_time:%f\tmax_event_size:%ld\n";
                 if (s.stats_used)
                     lpio_write(e, "model-net-category-test", sfmt(line, (long)g, (long)s.send_count, (long)s.send_bytes, s.send_time,
@@ -607,7 +643,6 @@ void finalize(dfd_engine* e) {
             } else {
                 unsigned r = rep;
                 const PortState* ps = &e->res.port[(size_t)r * p.radix];
-                S.rng_draws += e->res.rh[r].rng_draws;
                 std::string rec;
                 int src_rel_id = r % p.num_routers, local_grp_id = r / p.num_routers;
                 for (int d = 0; d <= p.intra_grp_radix; d++) {  // indexes ports by router-local id (sic, dally:7010-7017)
@@ -629,6 +664,7 @@ void finalize(dfd_engine* e) {
             }
         }
     }
+    e->lpio_rendered = true;
 }
 
 // raw-lp-stats: the same per-LP statistics as C99 hex floats, for bit-exact comparison in the tests.  Built only
@@ -968,6 +1004,8 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     // hysteresis of the chunk bounds: a quarter of the smallest chunk lookahead of the link kind
     P->hyst_local = 0.25 * (p.router_delay + p.local_delay);
     P->hyst_global = 0.25 * (p.router_delay + p.global_delay);
+    P->act_budget = 4;
+    if (const char* ev = getenv("DFD_ACT_BUDGET")) P->act_budget = std::max(1, atoi(ev));
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
     P->traffic = o.traffic;
     P->num_msgs = o.num_messages;
@@ -1080,7 +1118,8 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
     if (make_device_params(e, &P)) return 1;
     if (check_in_degree(e)) return 1;
     // the device arrays are kept across runs of the same shape (cudaMalloc/cudaFree dominate a short run otherwise)
-    bool reuse = e->device_ready && e->dev.X.rank == e->rank && e->dev.X.world == e->world && e->world == 1 && e->dev_ensemble == e->ensemble;
+    // (a sharded engine keeps its exchange region too: the peers' CUDA-IPC mappings of it stay valid, dfd_engine_ipc_ready)
+    bool reuse = e->device_ready && e->dev.X.rank == e->rank && e->dev.X.world == e->world && e->dev_ensemble == e->ensemble;
     if (reuse) {
         const DfdHostTopo& T = e->topo;
         const std::vector<int>* tabs[] = {&T.loc_off, &T.loc_port, &T.loc_dest, &T.lout_lane, &T.lin_src, &T.gs_port, &T.gs_group, &T.gdest, &T.gout_lane, &T.gin_src, &T.gin_port, &T.routed_off, &T.routed_lid};
@@ -1095,7 +1134,9 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
                 Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap;
     }
     if (reuse) {
+        const int budget = e->dev.P.act_budget;  // chosen by dfd_device_create from the grid it sized
         e->dev.P = P;
+        if (!getenv("DFD_ACT_BUDGET")) e->dev.P.act_budget = budget;
     } else {
         if (e->device_ready) {
             dfd_device_destroy(&e->dev);
@@ -1198,6 +1239,12 @@ int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world) {
     if (!e->uploaded) return fail(e, "ipc_import: engine_upload has not been called");
     if (dfd_device_ipc_import(&e->dev, handles, world)) return fail(e, "%s", e->dev.error);
     return 0;
+}
+int dfd_engine_ipc_ready(const dfd_engine* e) {
+    if (!e->uploaded) return 0;
+    for (int k = 0; k < e->dev.X.world; k++)
+        if (!e->dev.X.base[k]) return 0;
+    return 1;
 }
 namespace {
 struct PartHeader {
@@ -1324,6 +1371,7 @@ int dfd_tw_run(dfd_engine* e, void* stream) {
 int dfd_lp_io_flush(dfd_engine* e, const char* directory) {
     if (!e->finished) return fail(e, "lp_io_flush: the engine has not finished a run");
     if (mkdir(directory, 0775) != 0 && errno != EEXIST) return fail(e, "cannot create %s: %s", directory, strerror(errno));
+    render_lpio(e);
     build_raw(e);
     std::vector<LpioFile> files = e->lpio;
     files.push_back({"raw-lp-stats", e->raw});

@@ -282,6 +282,7 @@ struct DfdParams {
     int cslots, kslots;                // records per router in ring_c / ring_k
     int rpool_cap;
     int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
+    int act_budget;                    // router events after which an activation publishes its bounds even if more would be safe
 };
 
 struct DfdSeedConsts {  // CLCG4 constants: moduli, default seed, a^(2^(31+41)) mod m (stream jump)

@@ -118,6 +118,9 @@ int dfd_engine_set_ensemble(dfd_engine* e, int simulations);
 int dfd_engine_set_partition(dfd_engine* e, int rank, int world);
 int dfd_engine_ipc_export(dfd_engine* e, void* handle64);
 int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world);
+/* 1 when every peer's exchange region is mapped: a re-upload of the same shape keeps the device arrays and the mappings,
+ * so the handle exchange is needed only after the first upload (or a change of shape). */
+int dfd_engine_ipc_ready(const dfd_engine* e);
 long long dfd_engine_partition_bytes(const dfd_engine* e);
 /* ownership arithmetic: out4 = {first node, end node, first router, end router} of `rank` */
 int dfd_partition_bounds(int num_groups, int routers_per_group, int cns_per_router, int rank, int world, int* out4);

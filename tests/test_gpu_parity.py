@@ -253,7 +253,7 @@ def test_ensemble_matches_solo_runs(tmp_path):
         s = codes_b200.run_synthetic(CONF1056, lp_io_dir=solo, **v)
         assert sums[i].events == s.events and sums[i].total_hops == s.total_hops
         assert oracle_util.read_dir(dirs[i]) == oracle_util.read_dir(solo), i
-        assert sums[i].grid_blocks * len(variants) <= 4 * sums[i].num_sms  # all members are co-resident
+        assert sums[i].grid_blocks * len(variants) <= 16 * sums[i].num_sms  # all members are co-resident (16 one-warp blocks per SM)
 
 
 def test_terminal_runs_ahead_of_its_link(tmp_path):

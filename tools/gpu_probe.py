@@ -80,8 +80,10 @@ if __name__ == "__main__":
         perf(C1056, num_messages=100)
         perf(C8K, num_messages=20)
         perf(C8K, num_messages=20, traffic=3)
-    if "big" in what:
+    if "big" in what or "big131" in what:
         big(64, 2, "minimal", 1, 10)
+        big(64, 2, "prog-adaptive", 1, 10)
         big(64, 2, "prog-adaptive", 3, 10)
+    if "big" in what or "big1m" in what:
         big(128, 4, "minimal", 1, 5)
     sys.exit(1 if rc else 0)
