@@ -238,14 +238,9 @@ def main():
     sampler.start()
     kernel_ms = device_timed(eng, stream, flush, fence, sharded, args.steps, 0)
     clocks = sampler.stop()
-    eng.finish(stream)
-    if sharded:
-        parts = [None] * world
-        dist.gather_object(eng.export_partition(), parts if rank == 0 else None, dst=0)
-        if rank == 0:
-            for k in range(1, world):
-                eng.import_partition(parts[k])
-            eng.finalize()
+    fence()  # every rank's event loop is over
+    eng.finish(stream)  # sharded: rank 0 reads every partition's statistics over the CUDA-IPC mappings
+    fence()
     s = eng.summary()
     meta = [s.events, s.finished_packets, s.total_hops, s.finished_chunks, s.activations] if rank == 0 or not sharded else [0] * 5
     if sharded:

@@ -96,6 +96,7 @@ ABI = [
     ("dfd_engine_ipc_export", _I, [_P, _P]),
     ("dfd_engine_ipc_import", _I, [_P, _P, _I]),
     ("dfd_engine_ipc_ready", _I, [_P]),
+    ("dfd_engine_attach_local_peers", _I, [_P, ctypes.POINTER(_P), _I]),
     ("dfd_engine_partition_bytes", _LL, [_P]),
     ("dfd_partition_bounds", _I, [_I, _I, _I, _I, _I, ctypes.POINTER(_I)]),
     ("dfd_engine_export_partition", _I, [_P, _P, _LL]),
@@ -365,21 +366,49 @@ def sharded_tw_run(eng, dist, stream=None):
     dist.barrier()  # every rank's state is initialised before any kernel starts writing to its neighbours
     try:
         eng.run(stream)
-        eng.finish(stream)
-        blob = eng.export_partition()
+        torch.cuda.synchronize()
     except EngineError as ex:
-        err, blob = ex, None
+        err = ex
+    dist.barrier()  # every rank's event loop is over: rank 0 may read the partitions
+    try:
+        if err is None:
+            eng.finish(stream)  # rank 0: gathers every partition over the IPC mappings + final handlers
+    except EngineError as ex:
+        err = ex
     oks = [None] * world
-    dist.all_gather_object(oks, err is None)
+    dist.all_gather_object(oks, err is None)  # also keeps the partitions alive until rank 0 has read them
     if not all(oks):
         raise err or EngineError("group-sharded run: another rank reported a device error")
-    parts = [None] * world
-    dist.gather_object(blob if rank != 0 else None, parts if rank == 0 else None, dst=0)
-    if rank == 0:
-        for k in range(1, world):
-            eng.import_partition(parts[k])
-        eng.finalize()
-    dist.barrier()
+
+
+def run_sharded_local(conf_path, world, lp_io_dir=None, **opts):
+    """The group-sharded engine with all `world` ranks inside this process on ONE GPU (one engine and CUDA stream per rank,
+    the grids sized to be co-resident): the cross-rank code path without a second GPU.  Returns the merged Summary."""
+    import torch
+    engines, streams = [], [torch.cuda.Stream() for _ in range(world)]
+    try:
+        for k in range(world):
+            e = Engine()
+            engines.append(e)
+            e.setup(conf_path, make_opts(**opts))
+            e.set_partition(k, world)
+            e.set_ensemble(world)
+            e.upload(streams[k].cuda_stream)
+        arr = (_P * world)(*[e._h for e in engines])
+        for e in engines:
+            e._ck(e._lib.dfd_engine_attach_local_peers(e._h, arr, world))
+        torch.cuda.synchronize()
+        for k, e in enumerate(engines):
+            e.run(streams[k].cuda_stream)
+        torch.cuda.synchronize()
+        for k in range(world - 1, -1, -1):
+            engines[k].finish(streams[k].cuda_stream)
+        if lp_io_dir:
+            engines[0].lp_io_flush(lp_io_dir)
+        return engines[0].summary()
+    finally:
+        for e in engines:
+            e.close()
 
 
 def run_sharded(conf_path, dist, lp_io_dir=None, stream=None, **opts):

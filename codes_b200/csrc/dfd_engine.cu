@@ -222,7 +222,6 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     dev->nrmax = gmax * P.a;
     dev->ntmax = dev->nrmax * P.p;
     const size_t NT = (size_t)dev->ntl, NR = (size_t)dev->nrl, NRX = (size_t)dev->nrmax, NTX = (size_t)dev->ntmax, radix = (size_t)P.radix;
-    if (dalloc(dev, &A.node, NT)) return 1;
     if (dalloc(dev, &A.nev, NT * P.nev_cap)) return 1;
     if (dalloc(dev, &A.sq, NT * P.nsq_cap)) return 1;
     if (dalloc(dev, &A.mq, NT * P.nsq_cap)) return 1;
@@ -233,8 +232,6 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.ptab, NT * (size_t)P.nreasm_cap)) return 1;
     if (dalloc(dev, &A.ncin_tail, NT)) return 1;
     if (dalloc(dev, &A.nkin_tail, NT)) return 1;
-    if (dalloc(dev, &A.rh, NR)) return 1;
-    if (dalloc(dev, &A.port, NR * radix)) return 1;
     if (dalloc(dev, &A.portq, NR * radix)) return 1;
     if (dalloc(dev, &A.skey, NR * radix)) return 1;
     if (dalloc(dev, &A.ckey, NR * radix)) return 1;
@@ -268,11 +265,25 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     off = align256(off + NTX * sizeof(unsigned long long));
     size_t o_al = off;
     off = align256(off + NTX * sizeof(unsigned long long));
+    // ... and the per-LP statistics (read by rank 0 over the same mapping when the run is over)
+    size_t o_node = off;
+    off = align256(off + NTX * sizeof(NodeState));
+    size_t o_rh = off;
+    off = align256(off + NRX * sizeof(RouterHdr));
+    size_t o_port = off;
+    off = align256(off + NRX * radix * sizeof(PortState));
+    size_t o_cnt = off;
+    off = align256(off + 64 * sizeof(unsigned long long));
     char* xr = nullptr;
     if (dalloc(dev, &xr, off)) return 1;
     dev->xregion = xr;
     dev->xregion_bytes = off;
     dev->x_ack_off = o_ac;
+    dev->x_cnt_off = o_cnt;
+    A.node = (NodeState*)(xr + o_node);
+    A.rh = (RouterHdr*)(xr + o_rh);
+    A.port = (PortState*)(xr + o_port);
+    A.counters = (unsigned long long*)(xr + o_cnt);
     A.ctrl = (DfdCtrl*)xr;
     A.cw_c = (unsigned long long*)(xr + o_cwc);
     A.cw_k = (unsigned long long*)(xr + o_cwk);
@@ -284,7 +295,6 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     for (int k = 0; k < DFD_MAX_RANKS; k++) dev->X.base[k] = nullptr;
     dev->X.base[rank] = xr;
     dev->X.local_base = xr;
-    if (dalloc(dev, &A.counters, 64)) return 1;
     // connection tables
     std::vector<const std::vector<int>*> tabs = topo_tables(T);
     const int** slots[] = {&A.loc_off, &A.loc_port, &A.loc_dest, &A.lout_lane, &A.lin_src, &A.gs_port, &A.gs_group, &A.gdest, &A.gout_lane, &A.gin_src, &A.gin_port, &A.routed_off, &A.routed_lid};
@@ -389,33 +399,63 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t st) {
     return 0;
 }
 
-int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st) {
+int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st, int mode) {
     const DfdParams& P = dev->P;
     const DfdArrays& A = dev->A;
     const DfdPeers& X = dev->X;
-    const size_t nt = (size_t)dev->ntl, nr = (size_t)dev->nrl;
     out->node.resize(P.NT);
     out->rh.resize(P.NR);
     out->port.resize((size_t)P.NR * P.radix);
     out->ack_count.resize(P.NT);
     out->ack_first.resize(P.NT);
     out->ack_last.resize(P.NT);
-    CK(cudaMemcpyAsync(out->node.data() + X.n0, A.node, sizeof(NodeState) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->rh.data() + X.r0, A.rh, sizeof(RouterHdr) * nr, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->port.data() + (size_t)X.r0 * P.radix, A.port, sizeof(PortState) * nr * P.radix, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->ack_count.data() + X.n0, A.ack_count, sizeof(unsigned) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->ack_first.data() + X.n0, A.ack_first, sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->ack_last.data() + X.n0, A.ack_last, sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(out->counters, A.counters, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost, st));
-    DfdCtrl ctrl;
-    CK(cudaMemcpyAsync(&ctrl, A.ctrl, sizeof ctrl, cudaMemcpyDeviceToHost, st));
+    out->d2h_bytes = 0;
+    DfdCtrl ctrl[DFD_MAX_RANKS];
+    unsigned long long cnt[DFD_MAX_RANKS][64];
+    const int k0 = mode == DFD_DL_ALL ? 0 : X.rank, k1 = mode == DFD_DL_ALL ? X.world : X.rank + 1;
+    for (int k = k0; k < k1; k++) {
+        // every array of the statistics sits at the same offset of every rank's exchange region
+        const char* base = X.base[k];
+        if (!base) {
+            snprintf(dev->error, sizeof dev->error, "download: the exchange region of rank %d is not mapped", k);
+            return 1;
+        }
+        auto at = [&](const void* local) { return base + ((const char*)local - X.local_base); };
+        DfdPeers Y;
+        dfd_partition(P.G, P.a, P.p, k, X.world, &Y);
+        const size_t nt = (size_t)(Y.n1 - Y.n0), nr = (size_t)(Y.r1 - Y.r0);
+        if (mode != DFD_DL_CTRL) {
+            CK(cudaMemcpyAsync(out->node.data() + Y.n0, at(A.node), sizeof(NodeState) * nt, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->rh.data() + Y.r0, at(A.rh), sizeof(RouterHdr) * nr, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->port.data() + (size_t)Y.r0 * P.radix, at(A.port), sizeof(PortState) * nr * P.radix, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->ack_count.data() + Y.n0, at(A.ack_count), sizeof(unsigned) * nt, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->ack_first.data() + Y.n0, at(A.ack_first), sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(out->ack_last.data() + Y.n0, at(A.ack_last), sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
+            out->d2h_bytes += sizeof(NodeState) * nt + sizeof(RouterHdr) * nr + sizeof(PortState) * nr * P.radix + (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * nt;
+        }
+        CK(cudaMemcpyAsync(cnt[k], at(A.counters), sizeof cnt[k], cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&ctrl[k], at(A.ctrl), sizeof(DfdCtrl), cudaMemcpyDeviceToHost, st));
+        out->d2h_bytes += sizeof cnt[k] + sizeof(DfdCtrl);
+    }
     CK(cudaStreamSynchronize(st));
-    out->counters[2] = ctrl.error;
-    out->counters[3] = ctrl.error_info;
-    out->counters[26] = ctrl.created;
-    out->counters[27] = ctrl.consumed;
-    out->d2h_bytes = sizeof(NodeState) * nt + sizeof(RouterHdr) * nr + sizeof(PortState) * nr * P.radix +
-                     (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * nt + sizeof(unsigned long long) * 64 + sizeof ctrl;
+    memset(out->counters, 0, sizeof out->counters);
+    for (int k = k0; k < k1; k++) {
+        for (int i = 0; i < 64; i++)
+            if (i == 24)
+                out->counters[i] = std::max(out->counters[i], cnt[k][i]);  // busiest warp
+            else
+                out->counters[i] += cnt[k][i];
+    }
+    out->counters[2] = out->counters[3] = 0;
+    for (int k = k0; k < k1; k++) {
+        out->counters[26] += ctrl[k].created;
+        out->counters[27] += ctrl[k].consumed;
+        // the first error: a rank's own error wins over the "a peer failed" notice it may have received
+        if (ctrl[k].error && (!out->counters[2] || (out->counters[2] == DFD_ERR_PEER_ERROR && ctrl[k].error != DFD_ERR_PEER_ERROR))) {
+            out->counters[2] = ctrl[k].error;
+            out->counters[3] = ctrl[k].error_info;
+        }
+    }
     return 0;
 }
 

@@ -194,6 +194,8 @@ struct dfd_engine {
     DfdHostResults res;
     dfd_summary sum;
     std::vector<LpioFile> lpio;
+    bool slice_downloaded = false;  // e->res holds this rank's per-LP statistics
+    bool gathered = false;          // ... and every other rank's (rank 0 of a sharded run after engine_finish)
     bool lpio_rendered = false;  // the lp-io text records are rendered on demand (render_lpio)
     std::string raw;
     unsigned long long h2d_bytes = 0;
@@ -1210,11 +1212,17 @@ static void profile_print(dfd_engine* e) {
 int dfd_engine_finish(dfd_engine* e, void* stream) {
     if (!e->uploaded) return fail(e, "engine_finish: engine_upload has not been called");
     memset(&e->sum, 0, sizeof e->sum);
-    if (dfd_device_download(&e->dev, &e->res, (cudaStream_t)stream)) return fail(e, "%s", e->dev.error);
+    // Sharded run: the per-LP statistics of every partition live in the exchange regions, so rank 0 reads all of them
+    // over its CUDA-IPC mappings (the caller has waited for every rank's event loop: stream sync + barrier) and runs the
+    // final handlers; the other ranks only check their own control block.
+    const int mode = e->world == 1 ? DFD_DL_OWN : (e->rank == 0 ? DFD_DL_ALL : DFD_DL_CTRL);
+    if (dfd_device_download(&e->dev, &e->res, (cudaStream_t)stream, mode)) return fail(e, "%s", e->dev.error);
     if (e->res.counters[2] != 0)
         return fail(e, "device error %llu (%s), info 0x%llx", e->res.counters[2], device_error_name(e->res.counters[2]), e->res.counters[3]);
     e->downloaded = true;
-    if (e->world > 1) return 0;  // sharded run: rank 0 merges the partitions, then calls dfd_engine_finalize
+    e->slice_downloaded = mode != DFD_DL_CTRL;
+    e->gathered = mode == DFD_DL_ALL;
+    if (mode == DFD_DL_CTRL) return 0;
     finalize(e);
     fill_summary_meta(e);
     profile_print(e);
@@ -1238,6 +1246,19 @@ int dfd_engine_ipc_export(dfd_engine* e, void* handle64) {
 int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world) {
     if (!e->uploaded) return fail(e, "ipc_import: engine_upload has not been called");
     if (dfd_device_ipc_import(&e->dev, handles, world)) return fail(e, "%s", e->dev.error);
+    return 0;
+}
+// Several ranks of a sharded run inside ONE process on one GPU (each engine sized with dfd_engine_set_ensemble(world)):
+// the peers' exchange regions are plain device pointers, no CUDA-IPC needed.  Runs the very same cross-rank code path.
+int dfd_engine_attach_local_peers(dfd_engine* e, dfd_engine* const* engines, int world) {
+    if (!e->uploaded) return fail(e, "attach_local_peers: engine_upload has not been called");
+    if (world != e->world) return fail(e, "attach_local_peers: %d engines for a world of %d", world, e->world);
+    for (int k = 0; k < world; k++) {
+        const dfd_engine* q = engines[k];
+        if (!q || !q->uploaded || q->world != world || q->rank != k) return fail(e, "attach_local_peers: engine %d is not rank %d of this run", k, k);
+        if (q->dev.xregion_bytes != e->dev.xregion_bytes) return fail(e, "attach_local_peers: engine %d has a different layout", k);
+        e->dev.X.base[k] = q->dev.xregion;
+    }
     return 0;
 }
 int dfd_engine_ipc_ready(const dfd_engine* e) {
@@ -1271,6 +1292,10 @@ long long dfd_engine_partition_bytes(const dfd_engine* e) {
 int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len) {
     if (!e->downloaded) return fail(e, "export_partition: engine_finish has not been called");
     if (len < dfd_engine_partition_bytes(e)) return fail(e, "export_partition: buffer too small");
+    if (!e->slice_downloaded) {  // engine_finish of a non-root rank fetches only the control block
+        if (dfd_device_download(&e->dev, &e->res, nullptr, DFD_DL_OWN)) return fail(e, "%s", e->dev.error);
+        e->slice_downloaded = true;
+    }
     const DfdPeers& X = e->dev.X;
     size_t nn = X.n1 - X.n0, nr = X.r1 - X.r0, radix = e->hp.radix;
     char* p = (char*)buf;
@@ -1315,6 +1340,7 @@ int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
     const size_t need = sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) + nr * (sizeof(RouterHdr) + radix * sizeof(PortState));
     if ((size_t)len < need) return fail(e, "import_partition: truncated buffer (%lld bytes, need %zu)", len, need);
     if (h.counters[2]) return fail(e, "rank %d reported device error %llu (%s)", h.rank, h.counters[2], device_error_name(h.counters[2]));
+    if (e->gathered) return 0;  // engine_finish has already read this partition over the peer mapping
 #define GET(vec, off, cnt)                                   \
     memcpy((vec).data() + (off), p, (cnt) * sizeof((vec)[0])); \
     p += (cnt) * sizeof((vec)[0]);
@@ -1345,7 +1371,6 @@ void dfd_abi_sizes(int* summary_bytes, int* synthetic_opts_bytes) {
 }
 
 int dfd_engine_set_ensemble(dfd_engine* e, int simulations) {
-    if (e->world > 1 && simulations > 1) return fail(e, "engine_set_ensemble: a group-sharded engine owns its GPU");
     e->ensemble = simulations > 1 ? simulations : 1;
     return 0;
 }

@@ -113,14 +113,21 @@ int dfd_engine_set_ensemble(dfd_engine* e, int simulations);
  * codes_mapping()'s block mapping of LPs to MPI ranks, src/util/codes_mapping.c:78-86, with ROSS moving remote
  * events over MPI).  Rank k owns the dragonfly groups [k*G/world, (k+1)*G/world).  Sequence on every rank:
  *   set_partition -> engine_upload -> ipc_export -> (all-gather the 64-byte handles) -> ipc_import -> (barrier)
- *   -> engine_run -> engine_finish -> export_partition -> (gather on rank 0) -> import_partition x (world-1)
- *   -> engine_finalize (rank 0) -> lp_io_flush / report_stats (rank 0). */
+ *   -> engine_run -> (wait for the stream, barrier: every rank's event loop is over) -> engine_finish
+ *   -> lp_io_flush / report_stats (rank 0).
+ * engine_finish on rank 0 reads the per-LP statistics of EVERY partition over the CUDA-IPC mappings and runs the final
+ * handlers; on the other ranks it only checks the rank's own control block.  export_partition / import_partition /
+ * engine_finalize remain for callers that move the partitions themselves (e.g. over MPI): they are no-ops after a
+ * gathering engine_finish. */
 int dfd_engine_set_partition(dfd_engine* e, int rank, int world);
 int dfd_engine_ipc_export(dfd_engine* e, void* handle64);
 int dfd_engine_ipc_import(dfd_engine* e, const void* handles, int world);
 /* 1 when every peer's exchange region is mapped: a re-upload of the same shape keeps the device arrays and the mappings,
  * so the handle exchange is needed only after the first upload (or a change of shape). */
 int dfd_engine_ipc_ready(const dfd_engine* e);
+/* All ranks of a sharded run as engines of ONE process on one GPU (each sized with dfd_engine_set_ensemble(world)): replaces
+ * ipc_export / ipc_import; engines[k] is rank k.  Exercises the cross-rank path where only one GPU is available. */
+int dfd_engine_attach_local_peers(dfd_engine* e, dfd_engine* const* engines, int world);
 long long dfd_engine_partition_bytes(const dfd_engine* e);
 /* ownership arithmetic: out4 = {first node, end node, first router, end router} of `rank` */
 int dfd_partition_bounds(int num_groups, int routers_per_group, int cns_per_router, int rank, int world, int* out4);

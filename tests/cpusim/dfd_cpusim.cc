@@ -29,6 +29,15 @@ extern "C" cudaError_t cudaGetDeviceCount(int* count) {
     return cudaSuccess;
 }
 extern "C" cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+extern "C" cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) {
+    *p = malloc(bytes);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+extern "C" cudaError_t cudaFreeHost(void* p) {
+    free(p);
+    return cudaSuccess;
+}
+extern "C" cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 
 namespace {
 struct Rank {
@@ -321,7 +330,7 @@ done:
     return 0;
 }
 
-int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t) {
+int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t, int) {
     const DfdParams& P = dev->P;
     out->node.resize(P.NT);
     out->rh.resize(P.NR);

@@ -4,6 +4,8 @@ must be byte-identical; `Net Events Processed` must be equal."""
 import hashlib
 import json
 import os
+import subprocess
+import sys
 
 import pytest
 
@@ -305,3 +307,31 @@ def test_engine_matches_oracle_parallel_local_links(tmp_path, name, radix, conns
     conf = make_topology(tmp_path, radix, conns, routing, switch_conns=2)
     s, o, g, r = run_both(tmp_path, conf, **opts)
     assert_identical(s, o, g, r)
+
+
+@pytest.mark.parametrize("world,conf,opts", [(2, CONF72, dict(num_messages=20)), (3, CONF72, dict(num_messages=10, traffic=3)),
+                                             (4, CONF1056, dict(num_messages=10)), (2, CONF1056, dict(num_messages=5, payload_sz=10000)),
+                                             (8, CONF8K, dict(num_messages=3, traffic=3))])
+def test_group_sharded_ranks_on_one_gpu_match_oracle(tmp_path, world, conf, opts):
+    """The group-sharded engine with all ranks on this one GPU: cross-rank lanes, channel words, ACK statistics,
+    termination detection over several control blocks and rank 0's gather of the partitions must give the sequential
+    result bit for bit (the reference's analogue: --sync=1 vs --sync=3, tests/CMakeLists.txt:66-68).  The multi-process
+    CUDA-IPC variant of the same path is tests/mgpu_check.py (torchrun, needs >= 2 GPUs)."""
+    gdir, odir = str(tmp_path / "gpu"), str(tmp_path / "oracle")
+    s = codes_b200.run_sharded_local(conf, world, lp_io_dir=gdir, **opts)
+    o = oracle_util.run(conf, lp_io_dir=odir, **opts)
+    assert s.events == o.events
+    g, r = oracle_util.read_dir(gdir), oracle_util.read_dir(odir)
+    for name in r:
+        assert g[name] == r[name], f"{name} differs"
+
+
+def test_multi_process_sharding_when_two_gpus_are_present():
+    """torchrun with one process per GPU (CUDA-IPC exchange regions over NVLink): tests/mgpu_check.py."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "MGPU PARITY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

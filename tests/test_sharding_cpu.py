@@ -84,11 +84,15 @@ def test_partition_api_guards(engine_lib):
             e.export_partition()
 
 
-def test_ensemble_hint_is_for_unsharded_engines(engine_lib):
-    """dfd_engine_set_ensemble: engines that share one GPU; a group-sharded engine owns its GPU."""
+def test_ensemble_hint_and_local_peer_guards(engine_lib):
+    """dfd_engine_set_ensemble: engines that share one GPU (also the ranks of a sharded run held by one process);
+    attach_local_peers needs uploaded engines."""
     with codes_b200.Engine() as e:
         e.set_ensemble(8)
         e.set_ensemble(0)  # back to the default
         e.set_partition(1, 2)
-        with pytest.raises(codes_b200.EngineError, match="owns its GPU"):
-            e.set_ensemble(4)
+        e.set_ensemble(2)
+        import ctypes
+        arr = (ctypes.c_void_p * 2)(e._h, e._h)
+        assert e._lib.dfd_engine_attach_local_peers(e._h, arr, 2) != 0
+        assert "engine_upload" in e._lib.dfd_last_error(e._h).decode()

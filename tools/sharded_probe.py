@@ -31,13 +31,10 @@ for it in range(2):
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     times.append(float(dt[0]))
+torch.cuda.synchronize(); dist.barrier()
 eng.finish()
-parts = [None] * world
-dist.gather_object(eng.export_partition(), parts if rank == 0 else None, dst=0)
+dist.barrier()
 if rank == 0:
-    for k in range(1, world):
-        eng.import_partition(parts[k])
-    eng.finalize()
     s = eng.summary()
     dt = times[-1]
     print(f"[{world} GPUs sharded] {os.path.basename(conf)} {opts}: events {s.events} packets {s.finished_packets} windows {s.windows} "
