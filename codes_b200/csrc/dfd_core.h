@@ -248,6 +248,7 @@ struct Ctx {
     double* iblk;   // [2][p]: bounds of the (empty) terminal lanes, set at the start of every router phase
     double rclock;  // lower bound on the router's next event
     bool nothing_pending;  // no event is pending anywhere in the group and no external lane has a finite bound
+    double ev_min;         // earliest pending event of the group as of the last router-phase scan (events only, no bounds)
     double node_floor;     // earliest pending event of any terminal of the group (as of the last bounds pass)
     double node_push_min;  // earliest record the router handed to a terminal since then (lane 0)
     // --- per-lane accounting of this activation
@@ -1775,7 +1776,8 @@ DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
         // `hard`: the same minimum without the bounds of empty TERMINAL lanes.  Those bounds are derived from the
         // router's own clock and would let it creep upwards round by round; the next router event, however, can only
         // come from a pending router event, an external lane, or an event pending at one of the terminals.
-        double hard = DFD_TS_BIG;
+        double hard = DFD_TS_BIG;  // bounds of the empty EXTERNAL lanes
+        double evm = DFD_TS_BIG;   // pending events: heads of the non-empty lanes, R_SEND timers
         LANE_FOR(j, radix) {
             const LaneCtl L = c.lane[j];
             const bool ext = j < P.ext;
@@ -1784,22 +1786,29 @@ DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
                 best = k;
                 bidx = j;
             }
-            if (ext || L.chead != L.ctail) hard = mind(hard, k.ts);
+            if (L.chead != L.ctail)
+                evm = mind(evm, k.ts);
+            else if (ext)
+                hard = mind(hard, k.ts);
             k = c.kkey[j];
             if (key_lt(k, best)) {
                 best = k;
                 bidx = radix + j;
             }
-            if (ext || L.khead != L.ktail) hard = mind(hard, k.ts);
+            if (L.khead != L.ktail)
+                evm = mind(evm, k.ts);
+            else if (ext)
+                hard = mind(hard, k.ts);
             k = c.skey[j];
             if (key_lt(k, best)) {
                 best = k;
                 bidx = 2 * radix + j;
             }
-            hard = mind(hard, k.ts);
+            evm = mind(evm, k.ts);
         }
         warp_argmin_key(best, bidx);
-        hard = mind(warp_min_d(mind(hard, c.node_push_min)), c.node_floor);
+        c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
+        hard = mind(warp_min_d(hard), c.ev_min);
         c.rclock = maxd(best.ts, mind(hard, DFD_TS_BIG));
         c.nothing_pending = !(hard < DFD_TS_BIG);
         if (bidx >= 3 * radix) break;
@@ -1922,19 +1931,27 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     res.nexec = 0;
     RouterHdr hd = A.rh[rl];  // lane 0's working copy; written back once
     // ---- (1) poll the channel words of the external lanes
+    // A changed word is RELEVANT only if the lane was empty and its old bound did not lie beyond the group's earliest
+    // pending event (hd.ev_min): only such a bound can have been what the group was waiting for, and only such a change
+    // can move the group's clock.  Everything else (a neighbour that is ahead announcing that it is further ahead, records
+    // queueing up behind the head of a lane) is absorbed into the lane state and acted upon by the next full activation.
+    // Outputs that stay stale because of this all lie beyond ev_min + a credit delay, so they can never be what the
+    // LP holding the globally earliest event waits for ("relevance filter").
     const bool first = hd.clock < 0.0;
     bool changed = hd.more != 0 || first;
+    const double ev_min = hd.ev_min;
     {
         const unsigned long long* cwc = A.cw_c + (size_t)rl * P.radix;
         const unsigned long long* cwk = A.cw_k + (size_t)rl * P.radix;
         LANE_FOR(j, P.ext) {
             unsigned long long w = ld_strong64(&cwc[j]);
             unsigned long long v = ld_strong64(&cwk[j]);
-            if (w != c.seen_c[j]) {
-                changed = true;
+            const unsigned long long w0 = c.seen_c[j];
+            if (w != w0) {
                 c.seen_c[j] = w;
                 LaneCtl& L = c.lane[j];
                 bool was_empty = L.chead == L.ctail;
+                if (was_empty && cw_bound(w0) <= ev_min) changed = true;
                 L.ctail = cw_tail(w, L.chead);
                 if (was_empty) {
                     if (L.chead != L.ctail)
@@ -1943,11 +1960,12 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
                         c.ckey[j] = mk_key(cw_bound(w), 0, 0);
                 }
             }
-            if (v != c.seen_k[j]) {
-                changed = true;
+            const unsigned long long v0 = c.seen_k[j];
+            if (v != v0) {
                 c.seen_k[j] = v;
                 LaneCtl& L = c.lane[j];
                 bool was_empty = L.khead == L.ktail;
+                if (was_empty && cw_bound(v0) <= ev_min) changed = true;
                 L.ktail = cw_tail(v, L.khead);
                 if (was_empty) {
                     if (L.khead != L.ktail) {
@@ -2041,6 +2059,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     if (IS_LANE0()) {
         hd.clock = c.rclock;
         hd.more = more ? 1u : 0u;
+        hd.ev_min = c.ev_min;  // exact after a round that executed nothing (the fixed-point exit); unused after `more`
         if (total) hd.activations++;
         A.rh[rl] = hd;
     }

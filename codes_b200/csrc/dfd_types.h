@@ -154,6 +154,8 @@ struct __attribute__((aligned(16))) RouterHdr {
     uint32_t more;       // the last activation stopped on its event budget: safe events may remain
     uint32_t pad0;
     unsigned long long activations;  // activations that executed at least one event
+    double ev_min;       // earliest pending event of the group (router and terminals) when the last activation ended
+    double pad1;
 };
 
 // self-scheduled event of a node (svr + base LP + terminal fused), 48 bytes
