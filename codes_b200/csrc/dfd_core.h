@@ -387,6 +387,16 @@ DFD_FN unsigned lane_k_off(const DfdParams& P, int q) {
     return (unsigned)P.intra_radix * P.cap_l + (unsigned)P.global_radix * P.cap_g + (unsigned)(q - P.ext) * P.cap_tk;
 }
 DFD_FN unsigned lane_k_cap(const DfdParams& P, int q) { return q < P.intra_radix ? P.cap_l : q < P.ext ? P.cap_g : P.cap_tk; }
+// ring slot of record number `count` of chunk in-lane s / credit lane q: offset and capacity mask of every lane index come
+// from a small table (the same for all routers) instead of three-way branches at every use
+DFD_FN unsigned ring_c_idx(const DfdArrays& A, int s, unsigned count) {
+    const uint2 g = A.lgeo[2 * s];
+    return g.x + (count & g.y);
+}
+DFD_FN unsigned ring_k_idx(const DfdArrays& A, int q, unsigned count) {
+    const uint2 g = A.lgeo[2 * q + 1];
+    return g.x + (count & g.y);
+}
 
 DFD_FN unsigned long long cw_pack(double bound, unsigned count) {
     if (!(bound < DFD_TS_BIG)) bound = DFD_TS_BIG;
@@ -426,9 +436,8 @@ DFD_FN void push_chunk_to_router(Ctx& c, int q, unsigned d, const ChunkRec& rec)
     unsigned dl;
     int owner = router_home(c, d, &dl);
     LaneCtl& L = c.lane[q];
-    unsigned idx = L.sent_c & (lane_c_cap(P, s) - 1);
+    ChunkRec* slot = A.ring_c + (size_t)dl * P.cslots + ring_c_idx(A, s, L.sent_c);
     L.sent_c++;
-    ChunkRec* slot = A.ring_c + (size_t)dl * P.cslots + lane_c_off(P, s) + idx;
     if (owner != c.X->rank) {
         slot = on_rank(*c.X, slot, owner);
         c.wrote_remote = true;
@@ -446,9 +455,8 @@ DFD_FN void push_credit_to_router(Ctx& c, int s, unsigned u, unsigned port, doub
     unsigned ul;
     int owner = router_home(c, u, &ul);
     LaneCtl& L = c.lane[s];
-    unsigned idx = L.sent_k & (lane_k_cap(P, (int)port) - 1);
+    Key* slot = A.ring_k + (size_t)ul * P.kslots + ring_k_idx(A, (int)port, L.sent_k);
     L.sent_k++;
-    Key* slot = A.ring_k + (size_t)ul * P.kslots + lane_k_off(P, (int)port) + idx;
     if (owner != c.X->rank) {
         slot = on_rank(*c.X, slot, owner);
         c.wrote_remote = true;
@@ -490,7 +498,7 @@ DFD_FN void node_push_chunk(Ctx& c, int t, const ChunkRec& rec) {
     if (rec.ts >= P.ts_end) return;
     int s = P.ext + t;
     LaneCtl& L = c.lane[s];
-    ChunkRec* slot = c.ring_c + lane_c_off(P, s) + (L.ctail & (P.cap_tc - 1));
+    ChunkRec* slot = c.ring_c + ring_c_idx(*c.A, s, L.ctail);
     const int4* src = (const int4*)&rec;
 #pragma unroll
     for (int i = 0; i < 6; i++) st_cg16((int4*)slot + i, src[i]);
@@ -504,7 +512,7 @@ DFD_FN void node_push_credit(Ctx& c, int t, double ts, unsigned src, unsigned se
     int s = P.ext + t;
     LaneCtl& L = c.lane[s];
     Key rec = mk_key(ts, src | (vc << 30), seq);
-    st_cg16(c.ring_k + lane_k_off(P, s) + (L.ktail & (P.cap_tk - 1)), *(const int4*)&rec);
+    st_cg16(c.ring_k + ring_k_idx(*c.A, s, L.ktail), *(const int4*)&rec);
     if (L.khead == L.ktail) c.kkey[s] = mk_key(ts, src, seq);
     L.ktail++;
     c.ncreated++;
@@ -1168,14 +1176,25 @@ DFD_FN void loc_range(const DfdParams& P, const DfdArrays& A, int mylid, int lid
     *hi = A.loc_off[mylid * P.a + lid + 1];
 }
 // direct global connections to group g (get_connections_to_group): contiguous range of the by-dest-gid list
-DFD_FN void grp_range(const DfdParams& P, const DfdArrays& A, unsigned r, int g, int* lo, int* hi) {
-    const int* gg = A.gs_group + (size_t)r * P.h;
-    int l = 0;
-    while (l < P.h && gg[l] < g) l++;
+// (the by-gid list is sorted by destination group, unused slots hold INT_MAX at the end: lower bound by bisection)
+DFD_FN_OUTLINE int grp_range_find(const int* gg, int h, int g) {
+    int l = 0, n = h;
+    while (n > 0) {
+        int half = n >> 1;
+        if (gg[l + half] < g) {
+            l += half + 1;
+            n -= half + 1;
+        } else
+            n = half;
+    }
     int u = l;
-    while (u < P.h && gg[u] == g) u++;
-    *lo = l;
-    *hi = u;
+    while (u < h && gg[u] == g) u++;
+    return l | (u << 16);
+}
+DFD_FN void grp_range(const DfdParams& P, const DfdArrays& A, unsigned r, int g, int* lo, int* hi) {
+    int v = grp_range_find(A.gs_group + (size_t)r * P.h, P.h, g);
+    *lo = v & 0xFFFF;
+    *hi = v >> 16;
 }
 
 // a candidate list of next-hop connections, never materialised:
@@ -1768,6 +1787,7 @@ DFD_FN double empty_bound_k(const Ctx& c, int j) { return j < c.P->ext ? cw_boun
 // Every lane scans its share of the 3*radix entries, a warp argmin picks, lane 0 executes.
 DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
     const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
     const int radix = P.radix;
     unsigned nproc = 0;
     for (;;) {
@@ -1822,25 +1842,25 @@ DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
             check_order(c, &hd->last_ts, &hd->last_src, &hd->last_seq, best.ts, best.src, best.seq, kind != 2, c.r);
                 if (kind == 0) {
                 ChunkRec rec;
-                const ChunkRec* src = c.ring_c + lane_c_off(P, j) + (L.chead & (lane_c_cap(P, j) - 1));
+                const ChunkRec* src = c.ring_c + ring_c_idx(A, j, L.chead);
 #pragma unroll
                 for (int i = 0; i < 6; i++) ((int4*)&rec)[i] = ld_cg16((const int4*)src + i);
                 L.chead++;
                 c.lane[j].chead = L.chead;
                 if (L.chead != L.ctail) {
-                    const ChunkRec* nx = c.ring_c + lane_c_off(P, j) + (L.chead & (lane_c_cap(P, j) - 1));
+                    const ChunkRec* nx = c.ring_c + ring_c_idx(A, j, L.chead);
                     c.ckey[j] = key_from_int4(ld_cg16(nx));
                 } else
                     c.ckey[j] = mk_key(empty_bound_c(c, j), 0, 0);
                 count_ev(c.ev, EV_R_ARRIVE);
                 router_packet_receive(c, now, rec, j);
             } else if (kind == 1) {
-                const Key* src = c.ring_k + lane_k_off(P, j) + (L.khead & (lane_k_cap(P, j) - 1));
+                const Key* src = c.ring_k + ring_k_idx(A, j, L.khead);
                 Key rec = key_from_int4(ld_cg16(src));
                 L.khead++;
                 c.lane[j].khead = L.khead;
                 if (L.khead != L.ktail) {
-                    Key nx = key_from_int4(ld_cg16(c.ring_k + lane_k_off(P, j) + (L.khead & (lane_k_cap(P, j) - 1))));
+                    Key nx = key_from_int4(ld_cg16(c.ring_k + ring_k_idx(A, j, L.khead)));
                     nx.src &= DFD_GID_MASK;
                     c.kkey[j] = nx;
                 } else
@@ -1955,7 +1975,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
                 L.ctail = cw_tail(w, L.chead);
                 if (was_empty) {
                     if (L.chead != L.ctail)
-                        c.ckey[j] = key_from_int4(ld_cg16(c.ring_c + lane_c_off(P, j) + (L.chead & (lane_c_cap(P, j) - 1))));
+                        c.ckey[j] = key_from_int4(ld_cg16(c.ring_c + ring_c_idx(A, j, L.chead)));
                     else
                         c.ckey[j] = mk_key(cw_bound(w), 0, 0);
                 }
@@ -1969,7 +1989,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
                 L.ktail = cw_tail(v, L.khead);
                 if (was_empty) {
                     if (L.khead != L.ktail) {
-                        Key nx = key_from_int4(ld_cg16(c.ring_k + lane_k_off(P, j) + (L.khead & (lane_k_cap(P, j) - 1))));
+                        Key nx = key_from_int4(ld_cg16(c.ring_k + ring_k_idx(A, j, L.khead)));
                         nx.src &= DFD_GID_MASK;
                         c.kkey[j] = nx;
                     } else

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         if (w == 0 && nexec == 0 && (idle_passes & 7) == 1) {
             if (monitor_check(A, X, &last_consumed, &last_change_ns, timeout_ns, c)) break;
         }
+        if (nexec == 0 && P.idle_sleep_ns) __nanosleep((unsigned)P.idle_sleep_ns);
     }
     __syncwarp();
     if (lane < EV_NTYPES && s_ev[lane]) {
@@ -183,6 +184,28 @@ void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X) {
     X->r1 = X->grp_lo[rank + 1] * a;
     X->n0 = X->r0 * p;
     X->n1 = X->r1 * p;
+}
+
+// ring geometry by lane index (DfdArrays::lgeo): local links, global links, terminal lanes
+static void lane_geometry(const DfdParams& P, std::vector<uint2>* g) {
+    g->resize((size_t)P.radix * 2);
+    for (int j = 0; j < P.radix; j++) {
+        unsigned coff, ccap, koff, kcap;
+        if (j < P.intra_radix) {
+            coff = koff = (unsigned)j * P.cap_l;
+            ccap = kcap = P.cap_l;
+        } else if (j < P.ext) {
+            coff = koff = (unsigned)P.intra_radix * P.cap_l + (unsigned)(j - P.intra_radix) * P.cap_g;
+            ccap = kcap = P.cap_g;
+        } else {
+            coff = (unsigned)P.intra_radix * P.cap_l + (unsigned)P.global_radix * P.cap_g + (unsigned)(j - P.ext) * P.cap_tc;
+            koff = (unsigned)P.intra_radix * P.cap_l + (unsigned)P.global_radix * P.cap_g + (unsigned)(j - P.ext) * P.cap_tk;
+            ccap = P.cap_tc;
+            kcap = P.cap_tk;
+        }
+        (*g)[2 * j] = make_uint2(coff, ccap - 1);
+        (*g)[2 * j + 1] = make_uint2(koff, kcap - 1);
+    }
 }
 
 static std::vector<const std::vector<int>*> topo_tables(const DfdHostTopo& T) {
@@ -295,6 +318,14 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     for (int k = 0; k < DFD_MAX_RANKS; k++) dev->X.base[k] = nullptr;
     dev->X.base[rank] = xr;
     dev->X.local_base = xr;
+    {
+        std::vector<uint2> geo;
+        lane_geometry(P, &geo);
+        uint2* d = nullptr;
+        if (dalloc(dev, &d, geo.size())) return 1;
+        CK(cudaMemcpy(d, geo.data(), geo.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        A.lgeo = d;
+    }
     // connection tables
     std::vector<const std::vector<int>*> tabs = topo_tables(T);
     const int** slots[] = {&A.loc_off, &A.loc_port, &A.loc_dest, &A.lout_lane, &A.lin_src, &A.gs_port, &A.gs_group, &A.gdest, &A.gout_lane, &A.gin_src, &A.gin_port, &A.routed_off, &A.routed_lid};
@@ -333,6 +364,10 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     // publishing early lets the neighbours start.  With several groups per warp it is bound by throughput: the fixed
     // cost of an activation (poll, bounds, publish) is spread over more events.
     if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->grid ? 16 : 4;
+    // Idle warps of a throughput-bound run compete with the busy ones for instruction fetch: let them pause.  With a
+    // warp per group the poll latency is on the critical path: no pause.
+    dev->P.idle_sleep_ns = groups > (size_t)dev->grid ? 8000 : 0;
+    if (const char* ev = getenv("DFD_IDLE_SLEEP_NS")) dev->P.idle_sleep_ns = std::max(0, atoi(ev));
     return 0;
 }
 

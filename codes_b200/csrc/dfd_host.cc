@@ -1007,6 +1007,7 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->hyst_local = 0.25 * (p.router_delay + p.local_delay);
     P->hyst_global = 0.25 * (p.router_delay + p.global_delay);
     P->act_budget = 4;
+    P->idle_sleep_ns = 0;
     if (const char* ev = getenv("DFD_ACT_BUDGET")) P->act_budget = std::max(1, atoi(ev));
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
     P->traffic = o.traffic;
@@ -1136,9 +1137,10 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
                 Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap;
     }
     if (reuse) {
-        const int budget = e->dev.P.act_budget;  // chosen by dfd_device_create from the grid it sized
+        const int budget = e->dev.P.act_budget, idle_sleep = e->dev.P.idle_sleep_ns;  // chosen by dfd_device_create from the grid it sized
         e->dev.P = P;
         if (!getenv("DFD_ACT_BUDGET")) e->dev.P.act_budget = budget;
+        e->dev.P.idle_sleep_ns = idle_sleep;
     } else {
         if (e->device_ready) {
             dfd_device_destroy(&e->dev);

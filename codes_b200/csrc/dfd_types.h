@@ -284,6 +284,7 @@ struct DfdParams {
     int cslots, kslots;                // records per router in ring_c / ring_k
     int rpool_cap;
     int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
+    int idle_sleep_ns;                 // pause of a warp after a pass over its groups that executed nothing (0: poll again at once)
     int act_budget;                    // router events after which an activation publishes its bounds even if more would be safe
 };
 
@@ -347,6 +348,7 @@ struct DfdArrays {
     ChunkRec* ring_c;            // [NRmax][cslots]
     Key* ring_k;                 // [NRmax][kslots]
     DfdCtrl* ctrl;
+    const uint2* lgeo;      // [radix][2]  {ring offset, capacity - 1} of chunk in-lane j and of credit lane j (same for every router)
     // topology (read-only, global router ids)
     const int* loc_off;     // [a*a+1]   CSR over (my lid, dest lid) -> local ports
     const int* loc_port;    // [..]

@@ -72,6 +72,28 @@ void dfd_partition(int G, int a, int p, int rank, int world, DfdPeers* X) {
     X->n1 = X->r1 * p;
 }
 
+// ring geometry by lane index (DfdArrays::lgeo): local links, global links, terminal lanes
+static void lane_geometry(const DfdParams& P, std::vector<uint2>* g) {
+    g->resize((size_t)P.radix * 2);
+    for (int j = 0; j < P.radix; j++) {
+        unsigned coff, ccap, koff, kcap;
+        if (j < P.intra_radix) {
+            coff = koff = (unsigned)j * P.cap_l;
+            ccap = kcap = P.cap_l;
+        } else if (j < P.ext) {
+            coff = koff = (unsigned)P.intra_radix * P.cap_l + (unsigned)(j - P.intra_radix) * P.cap_g;
+            ccap = kcap = P.cap_g;
+        } else {
+            coff = (unsigned)P.intra_radix * P.cap_l + (unsigned)P.global_radix * P.cap_g + (unsigned)(j - P.ext) * P.cap_tc;
+            koff = (unsigned)P.intra_radix * P.cap_l + (unsigned)P.global_radix * P.cap_g + (unsigned)(j - P.ext) * P.cap_tk;
+            ccap = P.cap_tc;
+            kcap = P.cap_tk;
+        }
+        (*g)[2 * j] = uint2{coff, ccap - 1};
+        (*g)[2 * j + 1] = uint2{koff, kcap - 1};
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, int rank, int world, int) {
@@ -167,6 +189,13 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
         A.ack_first = (unsigned long long*)(xr + o_af);
         A.ack_last = (unsigned long long*)(xr + o_al);
         A.counters = halloc<unsigned long long>(R, 64);
+        {
+            std::vector<uint2> geo;
+            lane_geometry(P, &geo);
+            uint2* d = halloc<uint2>(R, geo.size());
+            memcpy(d, geo.data(), geo.size() * sizeof(uint2));
+            A.lgeo = d;
+        }
         A.loc_off = tcopy[0];
         A.loc_port = tcopy[1];
         A.loc_dest = tcopy[2];
