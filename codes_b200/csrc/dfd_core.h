@@ -214,9 +214,15 @@ DFD_FN void warp_argmin_key(Key& k, int& idx) {
     (void)idx;
 #endif
 }
+// warp-wide minimum of non-negative doubles: their bit patterns order like unsigned integers, so two redux.min steps do it
 DFD_FN double warp_min_d(double v) {
 #ifdef __CUDACC__
-    for (int o = 16; o > 0; o >>= 1) v = mind(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned long long tb = d2bits(v);
+    const unsigned hi = (unsigned)(tb >> 32), lo = (unsigned)tb;
+    const unsigned mhi = __reduce_min_sync(full, hi);
+    const unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xFFFFFFFFu);
+    v = bits2d(((unsigned long long)mhi << 32) | mlo);
 #endif
     return v;
 }
@@ -1943,13 +1949,11 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const DfdPeers& X = *c.X;
-    if (c.rl != rl || c.port == nullptr) ctx_bind_group(c, rl);
-    c.ncreated = 0;
-    c.nexec = 0;
-    c.wrote_remote = false;
     ActResult res;
     res.nexec = 0;
-    RouterHdr hd = A.rh[rl];  // lane 0's working copy; written back once
+    // ---- (1) poll the channel words of the external lanes.  The idle poll touches one 16-byte poll header and the two
+    // word arrays; the group's pointers are bound only when something has to be done.
+    const PollHdr ph = A.pollhdr[rl];
     // ---- (1) poll the channel words of the external lanes
     // A changed word is RELEVANT only if the lane was empty and its old bound did not lie beyond the group's earliest
     // pending event (hd.ev_min): only such a bound can have been what the group was waiting for, and only such a change
@@ -1957,49 +1961,57 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     // queueing up behind the head of a lane) is absorbed into the lane state and acted upon by the next full activation.
     // Outputs that stay stale because of this all lie beyond ev_min + a credit delay, so they can never be what the
     // LP holding the globally earliest event waits for ("relevance filter").
-    const bool first = hd.clock < 0.0;
-    bool changed = hd.more != 0 || first;
-    const double ev_min = hd.ev_min;
+    const bool first = (ph.flags & 2u) != 0;
+    bool changed = ph.flags != 0;  // continuation of an activation that stopped on its budget, or the very first one
+    const double ev_min = ph.ev_min;
     {
-        const unsigned long long* cwc = A.cw_c + (size_t)rl * P.radix;
-        const unsigned long long* cwk = A.cw_k + (size_t)rl * P.radix;
+        const size_t ro = (size_t)rl * P.radix;
+        const unsigned long long* cwc = A.cw_c + ro;
+        const unsigned long long* cwk = A.cw_k + ro;
+        unsigned long long* sc = A.seen_c + ro;
+        unsigned long long* sk = A.seen_k + ro;
         LANE_FOR(j, P.ext) {
             unsigned long long w = ld_strong64(&cwc[j]);
             unsigned long long v = ld_strong64(&cwk[j]);
-            const unsigned long long w0 = c.seen_c[j];
+            const unsigned long long w0 = sc[j];
+            const unsigned long long v0 = sk[j];
             if (w != w0) {
-                c.seen_c[j] = w;
-                LaneCtl& L = c.lane[j];
+                sc[j] = w;
+                LaneCtl& L = A.lane[ro + j];
                 bool was_empty = L.chead == L.ctail;
                 if (was_empty && cw_bound(w0) <= ev_min) changed = true;
                 L.ctail = cw_tail(w, L.chead);
                 if (was_empty) {
                     if (L.chead != L.ctail)
-                        c.ckey[j] = key_from_int4(ld_cg16(c.ring_c + ring_c_idx(A, j, L.chead)));
+                        A.ckey[ro + j] = key_from_int4(ld_cg16(A.ring_c + (size_t)rl * P.cslots + ring_c_idx(A, j, L.chead)));
                     else
-                        c.ckey[j] = mk_key(cw_bound(w), 0, 0);
+                        A.ckey[ro + j] = mk_key(cw_bound(w), 0, 0);
                 }
             }
-            const unsigned long long v0 = c.seen_k[j];
             if (v != v0) {
-                c.seen_k[j] = v;
-                LaneCtl& L = c.lane[j];
+                sk[j] = v;
+                LaneCtl& L = A.lane[ro + j];
                 bool was_empty = L.khead == L.ktail;
                 if (was_empty && cw_bound(v0) <= ev_min) changed = true;
                 L.ktail = cw_tail(v, L.khead);
                 if (was_empty) {
                     if (L.khead != L.ktail) {
-                        Key nx = key_from_int4(ld_cg16(c.ring_k + ring_k_idx(A, j, L.khead)));
+                        Key nx = key_from_int4(ld_cg16(A.ring_k + (size_t)rl * P.kslots + ring_k_idx(A, j, L.khead)));
                         nx.src &= DFD_GID_MASK;
-                        c.kkey[j] = nx;
+                        A.kkey[ro + j] = nx;
                     } else
-                        c.kkey[j] = mk_key(cw_bound(v), 0, 0);
+                        A.kkey[ro + j] = mk_key(cw_bound(v), 0, 0);
                 }
             }
         }
     }
     res.polled_change = warp_any(changed);
     if (!res.polled_change) return res;  // the previous activation ran to its fixed point on exactly this input
+    if (c.rl != rl || c.port == nullptr) ctx_bind_group(c, rl);
+    c.ncreated = 0;
+    c.nexec = 0;
+    c.wrote_remote = false;
+    RouterHdr hd = A.rh[rl];  // lane 0's working copy; written back once
     WARP_SYNC();
     long long t0 = CYC_NOW(), t1;
     // ---- (2) rounds of router phase + node phase until nothing more is safe (or the event budget is spent)
@@ -2080,6 +2092,11 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
         hd.clock = c.rclock;
         hd.more = more ? 1u : 0u;
         hd.ev_min = c.ev_min;  // exact after a round that executed nothing (the fixed-point exit); unused after `more`
+        PollHdr nph;
+        nph.ev_min = c.ev_min;
+        nph.flags = more ? 1u : 0u;
+        nph.pad = 0;
+        A.pollhdr[rl] = nph;
         if (total) hd.activations++;
         A.rh[rl] = hd;
     }

@@ -256,6 +256,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (dalloc(dev, &A.ncin_tail, NT)) return 1;
     if (dalloc(dev, &A.nkin_tail, NT)) return 1;
     if (dalloc(dev, &A.portq, NR * radix)) return 1;
+    if (dalloc(dev, &A.pollhdr, NR)) return 1;
     if (dalloc(dev, &A.skey, NR * radix)) return 1;
     if (dalloc(dev, &A.ckey, NR * radix)) return 1;
     if (dalloc(dev, &A.kkey, NR * radix)) return 1;

@@ -68,6 +68,9 @@ DFD_FN void init_router(const DfdParams& P, const DfdArrays& A, const DfdPeers& 
     h->grp = (uint16_t)(r / P.a);
     h->clock = -1.0;
     h->ev_min = 0.0;
+    A.pollhdr[rl].ev_min = 0.0;
+    A.pollhdr[rl].flags = 2u;
+    A.pollhdr[rl].pad = 0;
     h->pad1 = 0.0;
     for (int i = 0; i < 2 * P.p; i++) A.iblk[(size_t)rl * 2 * P.p + i] = 0.0;
 }

@@ -158,6 +158,13 @@ struct __attribute__((aligned(16))) RouterHdr {
     double pad1;
 };
 
+// what the idle poll of a group reads besides the channel words
+struct __attribute__((aligned(16))) PollHdr {
+    double ev_min;   // RouterHdr::ev_min
+    uint32_t flags;  // bit0: the last activation stopped on its event budget, bit1: never activated
+    uint32_t pad;
+};
+
 // self-scheduled event of a node (svr + base LP + terminal fused), 48 bytes
 struct __attribute__((aligned(16))) NodeEv {
     double ts;
@@ -325,6 +332,7 @@ struct DfdArrays {
     unsigned long long* ack_last;    // [NTmax]
     // routers: private state
     RouterHdr* rh;        // [NRl]
+    PollHdr* pollhdr;     // [NRl]
     PortState* port;      // [NRl][radix]
     PortQ* portq;         // [NRl][radix]
     Key* skey;            // [NRl][radix]  pending R_SEND of the port (ts = +inf: none)

@@ -148,6 +148,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
         A.rh = halloc<RouterHdr>(R, NR);
         A.port = halloc<PortState>(R, NR * radix);
         A.portq = halloc<PortQ>(R, NR * radix);
+        A.pollhdr = halloc<PollHdr>(R, NR);
         A.skey = halloc<Key>(R, NR * radix);
         A.ckey = halloc<Key>(R, NR * radix);
         A.kkey = halloc<Key>(R, NR * radix);
