@@ -1004,8 +1004,10 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     if (!(L > 0)) return fail(e, "this engine needs strictly positive link and credit delays (smallest is %g ns)", L);
     P->min_delay = L;
     // hysteresis of the chunk bounds: a quarter of the smallest chunk lookahead of the link kind
-    P->hyst_local = 0.25 * (p.router_delay + p.local_delay);
-    P->hyst_global = 0.25 * (p.router_delay + p.global_delay);
+    double hf = 0.25;
+    if (const char* ev = getenv("DFD_HYST_FRAC")) hf = std::min(0.9, std::max(0.0, atof(ev)));
+    P->hyst_local = hf * (p.router_delay + p.local_delay);
+    P->hyst_global = hf * (p.router_delay + p.global_delay);
     P->act_budget = 4;
     P->idle_sleep_ns = 0;
     if (const char* ev = getenv("DFD_ACT_BUDGET")) P->act_budget = std::max(1, atoi(ev));
