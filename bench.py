@@ -106,6 +106,27 @@ def measured_traffic():
     return None
 
 
+def parity_digest(eng, tmp):
+    """lp-io files of the engine's last run (the e2e leg: rank 0 holds the merged result of a sharded run) hashed against
+    the committed digests of the restatement oracle for this workload (tests/golden/131584_par_uniform_m10.json,
+    `python -m tests.make_golden --large 131584_par_uniform_m10`).  Outside every timed region."""
+    import hashlib
+    gold_path = os.path.join(ROOT, "tests", "golden", "131584_par_uniform_m10.json")
+    if not os.path.exists(gold_path):
+        return None
+    with open(gold_path) as f:
+        gold = json.load(f)
+    d = os.path.join(tmp, "lpio")
+    eng.lp_io_flush(d)
+    ok = eng.summary().events == gold["events"]
+    for name, digest in gold["sha256"].items():
+        if name == "summary.txt":
+            continue
+        with open(os.path.join(d, name), "rb") as f:
+            ok = ok and hashlib.sha256(f.read()).hexdigest() == digest
+    return bool(ok)
+
+
 def algorithmic_bytes(total_hops, chunks):
     return 832 * total_hops + 896 * chunks  # SURVEY 8(d)
 
@@ -274,6 +295,8 @@ def main():
         assert es.events == events_per_step
         h2d, d2h = es.h2d_bytes, es.d2h_bytes
 
+    digest_ok = parity_digest(eng, tmpdir.name) if rank == 0 else None
+
     t = torch.tensor([kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
     io = torch.tensor([h2d, d2h], dtype=torch.int64, device="cuda")
     if dist:
@@ -310,7 +333,9 @@ def main():
                          "note": "memory-latency-bound: one warp per router group walks dependent loads of LP state (DESIGN.md 5)"},
             "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": 2 * args.steps * world, "clocks": clocks}
+            "gpu_launches": 2 * args.steps * world, "clocks": clocks,
+            # every lp-io file of the (merged) result hashes to the CPU oracle's digest for this workload
+            "parity_digest_ok": digest_ok}
     if world == 1 and not args.no_extras:
         try:  # not the headline: the same network under the worst-case group permutation (BASELINE configs[3]'s traffic)
             e2 = codes_b200.Engine()

@@ -86,6 +86,7 @@ DFD_FN void ack_update(unsigned* cnt, unsigned long long* first, unsigned long l
     }
 }
 DFD_FN bool cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long v) { return atomicCAS(p, expect, v) == expect; }
+DFD_FN void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 DFD_FN void count_ev(unsigned* ev, int t) { atomicAdd(&ev[t], 1u); }
 DFD_FN bool warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 DFD_FN unsigned warp_sum_u(unsigned v) {
@@ -137,6 +138,7 @@ DFD_FN void ack_update(unsigned* cnt, unsigned long long* first, unsigned long l
     if (tb < *first) *first = tb;
     if (tb > *last) *last = tb;
 }
+DFD_FN void prefetch_l1(const void*) {}
 DFD_FN bool cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long v) {
     if (*p != expect) return false;
     *p = v;
@@ -2008,6 +2010,15 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     res.polled_change = warp_any(changed);
     if (!res.polled_change) return res;  // the previous activation ran to its fixed point on exactly this input
     if (c.rl != rl || c.port == nullptr) ctx_bind_group(c, rl);
+    if (P.prefetch) {
+        // Partitions far larger than L2: the handlers below walk port state, FIFO heads and terminal state through chains
+        // of dependent loads, each a DRAM miss.  Asking for all of it now, in parallel, turns the chain into one miss.
+        for (int j = DFD_LANE() * 2; j < P.radix; j += 64) {  // two 64-byte entries per line
+            prefetch_l1(&c.port[j]);
+            prefetch_l1(&c.pq[j]);
+        }
+        LANE_FOR(j, P.radix / 8 + 1) prefetch_l1(&c.lane[j * 8]);
+    }
     c.ncreated = 0;
     c.nexec = 0;
     c.wrote_remote = false;

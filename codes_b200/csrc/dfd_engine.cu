@@ -18,6 +18,8 @@
 #include "dfd_engine.h"
 #include "dfd_init.h"
 
+#define DFD_POOL_WARPS 16  // warps of one dfd_run_kernel_pool block: 16 x 32 threads x 128 registers = one SM's register file
+
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -57,8 +59,38 @@ __device__ bool monitor_check(const DfdArrays& A, const DfdPeers& X, unsigned lo
     return false;
 }
 
-// One warp per block.  MIN_BLOCKS trades registers for resident warps: <8> leaves 255 registers per thread for
-// partitions of up to 8 groups per SM (latency-bound), <16> caps at 128 registers for larger ones.
+// What a warp accumulates over its life and folds into the run counters when it leaves the event loop.
+struct WarpTally {
+    unsigned long long n_act = 0, n_prod = 0, n_exec = 0, passes = 0;
+    long long t_busy = 0, t_idle = 0;
+};
+__device__ __forceinline__ void tally_commit(const DfdArrays& A, const Ctx& c, const WarpTally& t) {
+    if (DFD_LANE() == 0) {
+        atomicAdd(&A.counters[1], t.n_prod);
+        atomicAdd(&A.counters[20], (unsigned long long)t.t_busy);
+        atomicAdd(&A.counters[21], (unsigned long long)t.t_idle);
+        atomicAdd(&A.counters[22], t.n_act);
+        atomicAdd(&A.counters[23], t.passes);
+        atomicMax(&A.counters[24], (unsigned long long)t.t_busy);
+        atomicAdd(&A.counters[25], t.n_exec);
+        for (int i = 0; i < 5; i++) atomicAdd(&A.counters[30 + i], (unsigned long long)c.cyc[i]);
+        atomicAdd(&A.counters[35], c.nrounds);
+    }
+}
+__device__ __forceinline__ void ctx_init(Ctx& c, const DfdParams* P, const DfdArrays* A, const DfdPeers* X, unsigned* ev) {
+    c.P = P;
+    c.A = A;
+    c.X = X;
+    c.ev = ev;
+    c.port = nullptr;
+    c.rl = 0xFFFFFFFFu;
+    for (int i = 0; i < 6; i++) c.cyc[i] = 0;
+    c.nrounds = 0;
+}
+
+// Latency-bound partitions (at most one group per resident warp): one warp per block, every warp owns its groups for
+// the whole run.  MIN_BLOCKS trades registers for resident warps: <8> leaves 255 registers per thread for partitions of
+// up to 8 groups per SM, <16> caps at 128 registers for larger ones.
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long timeout_ns) {
     __shared__ unsigned s_ev[EV_NTYPES];
@@ -66,18 +98,11 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
     if (lane < EV_NTYPES) s_ev[lane] = 0;
     __syncwarp();
     Ctx c;
-    c.P = &P;
-    c.A = &A;
-    c.X = &X;
-    c.ev = s_ev;
-    c.port = nullptr;
-    c.rl = 0xFFFFFFFFu;
-    for (int i = 0; i < 6; i++) c.cyc[i] = 0;
-    c.nrounds = 0;
+    ctx_init(c, &P, &A, &X, s_ev);
     const unsigned ngroups = (unsigned)(X.r1 - X.r0);
     const unsigned w = blockIdx.x, nw = gridDim.x;
-    unsigned long long n_act = 0, n_prod = 0, n_exec = 0, idle_passes = 0, passes = 0;
-    long long t_busy = 0, t_idle = 0;
+    WarpTally t;
+    unsigned long long idle_passes = 0;
     unsigned long long last_consumed = ~0ULL, last_change_ns = globaltimer_ns();
     for (;;) {
         long long c0 = clock64();
@@ -86,20 +111,20 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         unsigned nexec = 0;
         for (unsigned g = w; g < ngroups; g += nw) {
             ActResult a = group_activate(c, g);
-            n_act += a.polled_change ? 1 : 0;
-            n_prod += a.nexec ? 1 : 0;
+            t.n_act += a.polled_change ? 1 : 0;
+            t.n_prod += a.nexec ? 1 : 0;
             nexec += a.nexec;
         }
         long long c1 = clock64();
         if (nexec) {
-            t_busy += c1 - c0;
+            t.t_busy += c1 - c0;
             idle_passes = 0;
         } else {
-            t_idle += c1 - c0;
+            t.t_idle += c1 - c0;
             idle_passes++;
         }
-        n_exec += nexec;
-        passes++;
+        t.n_exec += nexec;
+        t.passes++;
         if (err | done) {
             if (err && w == 0 && lane == 0 && X.world > 1) propagate_error(A, X);
             break;
@@ -114,17 +139,83 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         atomicAdd(&A.counters[4 + lane], (unsigned long long)s_ev[lane]);
         atomicAdd(&A.counters[0], (unsigned long long)s_ev[lane]);
     }
-    if (lane == 0) {
-        atomicAdd(&A.counters[1], n_prod);
-        atomicAdd(&A.counters[20], (unsigned long long)t_busy);
-        atomicAdd(&A.counters[21], (unsigned long long)t_idle);
-        atomicAdd(&A.counters[22], n_act);
-        atomicAdd(&A.counters[23], passes);
-        atomicMax(&A.counters[24], (unsigned long long)t_busy);
-        atomicAdd(&A.counters[25], n_exec);
-        for (int i = 0; i < 5; i++) atomicAdd(&A.counters[30 + i], (unsigned long long)c.cyc[i]);
-        atomicAdd(&A.counters[35], c.nrounds);
+    tally_commit(A, c, t);
+}
+
+// Throughput-bound partitions (several groups per resident warp): one block of WARPS warps per SM owns a contiguous
+// slice of the groups, and its warps take turns on them -- a ticket counter deals the groups out round-robin, a lock word
+// per group keeps two warps off the same group.  A group whose activation runs long (a hot router, a burst of
+// arrivals) then holds up one warp, not the other groups a static assignment would have queued behind it; the group's
+// state still never leaves the SM, so its L1 lines stay where they are.  Lock and unlock are block-scope
+// acquire/release: the warps of a block share one L1, plain loads and stores of LP-private state are coherent there.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) dfd_run_kernel_pool(DfdParams P, DfdArrays A, DfdPeers X, unsigned long long timeout_ns) {
+    extern __shared__ unsigned s_lock[];  // [groups of this block]
+    __shared__ unsigned s_ev[EV_NTYPES];
+    __shared__ unsigned s_ticket;
+    const int lane = DFD_LANE();
+    const unsigned wib = threadIdx.x >> 5;
+    const unsigned ngroups = (unsigned)(X.r1 - X.r0);
+    const unsigned b = blockIdx.x, nb = gridDim.x;
+    const unsigned g0 = (unsigned)(((unsigned long long)ngroups * b) / nb), g1 = (unsigned)(((unsigned long long)ngroups * (b + 1)) / nb);
+    const unsigned ng = g1 - g0;
+    for (unsigned i = threadIdx.x; i < ng; i += blockDim.x) s_lock[i] = 0;
+    if (threadIdx.x < EV_NTYPES) s_ev[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_ticket = 0;
+    __syncthreads();
+    Ctx c;
+    ctx_init(c, &P, &A, &X, s_ev);
+    WarpTally t;
+    const bool monitor = b == 0 && wib == 0;
+    const unsigned per_pass = ng ? (ng + WARPS - 1) / WARPS : 0;
+    unsigned long long idle_passes = 0;
+    unsigned long long last_consumed = ~0ULL, last_change_ns = globaltimer_ns();
+    for (;;) {
+        long long c0 = clock64();
+        const unsigned long long err = ld_strong64(&A.ctrl->error), done = ld_strong64(&A.ctrl->done);
+        unsigned nexec = 0;
+        for (unsigned k = 0; k < per_pass; k++) {
+            unsigned i = 0;
+            if (lane == 0) {
+                i = atomicAdd(&s_ticket, 1u) % ng;
+                if (atomicExch_block(&s_lock[i], 1u) != 0u) i = 0xFFFFFFFFu;  // another warp is on it
+            }
+            i = __shfl_sync(0xFFFFFFFFu, i, 0);
+            if (i == 0xFFFFFFFFu) continue;
+            __threadfence_block();
+            ActResult a = group_activate(c, g0 + i);
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicExch_block(&s_lock[i], 0u);
+            t.n_act += a.polled_change ? 1 : 0;
+            t.n_prod += a.nexec ? 1 : 0;
+            nexec += a.nexec;
+        }
+        long long c1 = clock64();
+        if (nexec) {
+            t.t_busy += c1 - c0;
+            idle_passes = 0;
+        } else {
+            t.t_idle += c1 - c0;
+            idle_passes++;
+        }
+        t.n_exec += nexec;
+        t.passes++;
+        if (err | done) {
+            if (err && monitor && lane == 0 && X.world > 1) propagate_error(A, X);
+            break;
+        }
+        if (monitor && nexec == 0 && (idle_passes & 7) == 1) {
+            if (monitor_check(A, X, &last_consumed, &last_change_ns, timeout_ns, c)) break;
+        }
+        if (nexec == 0 && P.idle_sleep_ns) __nanosleep((unsigned)P.idle_sleep_ns);
     }
+    __syncthreads();
+    if (threadIdx.x < EV_NTYPES && s_ev[threadIdx.x]) {
+        atomicAdd(&A.counters[4 + threadIdx.x], (unsigned long long)s_ev[threadIdx.x]);
+        atomicAdd(&A.counters[0], (unsigned long long)s_ev[threadIdx.x]);
+    }
+    tally_commit(A, c, t);
 }
 
 // ================================================================================================
@@ -361,13 +452,38 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     if (ensemble > 1) slots_total = std::max<size_t>(1, slots_total / ensemble);  // the GPU is shared by `ensemble` engines
     dev->grid = (int)std::max<size_t>(1, std::min(groups, slots_total));
     if (const char* ev = getenv("DFD_GRID")) dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
+    // More groups than resident warps: one 16-warp block per SM whose warps share the block's groups (dfd_run_kernel_pool)
+    bool pool = groups > (size_t)dev->grid && ensemble <= 1 && !getenv("DFD_GRID") && !getenv("DFD_MINBLOCKS");
+    if (const char* ev = getenv("DFD_POOL")) pool = atoi(ev) != 0 && ensemble <= 1;
+    if (pool) {
+        constexpr int W = DFD_POOL_WARPS;
+        const int nb = (int)std::min<size_t>((size_t)dev->num_sms, (groups + W - 1) / W);
+        const size_t per_block = (groups + nb - 1) / nb;
+        const size_t smem = per_block * sizeof(unsigned);
+        const void* k = (const void*)dfd_run_kernel_pool<W>;
+        int fits = 0;
+        if (smem <= 160 * 1024) {
+            if (smem > 40 * 1024) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fits, (void (*)(DfdParams, DfdArrays, DfdPeers, unsigned long long))k, W * 32, smem));
+        }
+        if (fits >= 1) {
+            dev->kernel = k;
+            dev->block = W * 32;
+            dev->grid = nb;
+            dev->smem = smem;
+            dev->blocks_per_sm = 1;
+        }
+    }
+    dev->warps = dev->grid * (dev->block / 32);
     // Event budget of one activation.  With a warp per group the run is bound by the chain of dependent activations:
     // publishing early lets the neighbours start.  With several groups per warp it is bound by throughput: the fixed
     // cost of an activation (poll, bounds, publish) is spread over more events.
-    if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->grid ? 16 : 4;
+    if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->warps ? 16 : 4;
     // Idle warps of a throughput-bound run compete with the busy ones for instruction fetch: let them pause.  With a
     // warp per group the poll latency is on the critical path: no pause.
-    dev->P.idle_sleep_ns = groups > (size_t)dev->grid ? 8000 : 0;
+    dev->P.idle_sleep_ns = groups > (size_t)dev->warps ? 8000 : 0;
+    dev->P.prefetch = 0;  // measured on B200 at 131,584 and 1,050,624 terminals: no gain (-2 %), kept as a knob
+    if (const char* ev = getenv("DFD_PREFETCH")) dev->P.prefetch = atoi(ev);
     if (const char* ev = getenv("DFD_IDLE_SLEEP_NS")) dev->P.idle_sleep_ns = std::max(0, atoi(ev));
     return 0;
 }

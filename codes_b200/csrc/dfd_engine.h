@@ -85,6 +85,7 @@ struct DfdDevice {
     size_t bytes_allocated = 0, topo_bytes = 0;
     std::vector<size_t> topo_sizes;  // element counts of the uploaded tables (reuse check)
     int num_sms = 0, grid = 0, block = 0, blocks_per_sm = 0;
+    int warps = 0;  // resident warps of the event-loop kernel (grid x warps per block)
     size_t smem = 0;
     const void* kernel = nullptr;  // dfd_run_kernel instantiation in use
     char error[512] = {0};

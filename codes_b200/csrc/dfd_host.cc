@@ -1010,6 +1010,7 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->hyst_global = hf * (p.router_delay + p.global_delay);
     P->act_budget = 4;
     P->idle_sleep_ns = 0;
+    P->prefetch = 0;
     if (const char* ev = getenv("DFD_ACT_BUDGET")) P->act_budget = std::max(1, atoi(ev));
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
     P->traffic = o.traffic;
@@ -1139,10 +1140,11 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
                 Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap;
     }
     if (reuse) {
-        const int budget = e->dev.P.act_budget, idle_sleep = e->dev.P.idle_sleep_ns;  // chosen by dfd_device_create from the grid it sized
+        const int budget = e->dev.P.act_budget, idle_sleep = e->dev.P.idle_sleep_ns, prefetch = e->dev.P.prefetch;  // chosen by dfd_device_create from the grid it sized
         e->dev.P = P;
         if (!getenv("DFD_ACT_BUDGET")) e->dev.P.act_budget = budget;
         e->dev.P.idle_sleep_ns = idle_sleep;
+        e->dev.P.prefetch = prefetch;
     } else {
         if (e->device_ready) {
             dfd_device_destroy(&e->dev);
@@ -1193,8 +1195,8 @@ static void fill_summary_meta(dfd_engine* e) {
     S.num_routers = e->hp.total_routers;
     S.radix = e->hp.radix;
     const unsigned long long* C = e->res.counters;
-    S.cyc_busy = (double)C[20] / e->dev.grid;
-    S.cyc_idle = (double)C[21] / e->dev.grid;
+    S.cyc_busy = (double)C[20] / e->dev.warps;
+    S.cyc_idle = (double)C[21] / e->dev.warps;
     S.cyc_busy_max_warp = (double)C[24];
     S.activations = C[22];
     S.passes = C[23];
@@ -1206,11 +1208,11 @@ static void profile_print(dfd_engine* e) {
     const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
     for (int i = 0; i < EV_NTYPES; i++)
         if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu\n", names[i], C[4 + i]);
-    fprintf(stderr, "  warps %d, passes %llu, activations past the poll %llu, productive %llu, events/productive activation %.2f\n", e->dev.grid, C[23], C[22], C[1],
+    fprintf(stderr, "  warps %d, passes %llu, activations past the poll %llu, productive %llu, events/productive activation %.2f\n", e->dev.warps, C[23], C[22], C[1],
             C[1] ? (double)C[0] / C[1] : 0.0);
     fprintf(stderr, "  rounds %llu; cycles per warp inside activations: poll-tail %.0f, terminal bounds %.0f, router phase %.0f, node phase %.0f, publish %.0f\n", C[35],
-            (double)C[30] / e->dev.grid, (double)C[31] / e->dev.grid, (double)C[32] / e->dev.grid, (double)C[33] / e->dev.grid, (double)C[34] / e->dev.grid);
-    fprintf(stderr, "  cycles per warp: busy passes %.0f, idle passes %.0f, busiest warp %.0f\n", (double)C[20] / e->dev.grid, (double)C[21] / e->dev.grid, (double)C[24]);
+            (double)C[30] / e->dev.warps, (double)C[31] / e->dev.warps, (double)C[32] / e->dev.warps, (double)C[33] / e->dev.warps, (double)C[34] / e->dev.warps);
+    fprintf(stderr, "  cycles per warp: busy passes %.0f, idle passes %.0f, busiest warp %.0f\n", (double)C[20] / e->dev.warps, (double)C[21] / e->dev.warps, (double)C[24]);
 }
 
 int dfd_engine_finish(dfd_engine* e, void* stream) {

@@ -205,7 +205,12 @@ struct TermChunk {
 };
 
 // node = svr LP + model-net base LP + dragonfly-dally terminal LP of one compute node
-struct __attribute__((aligned(16))) NodeState {
+struct __attribute__((aligned(128))) NodeState {
+    // --- what the router's bounds pass reads of every terminal in every round: one 32-byte sector at the start of a line
+    double self_next;            // earliest timestamp among the self-scheduled events (nev list, mq); +inf: none
+    double terminal_available_time;
+    uint32_t cin_head, kin_head; // records consumed from the chunk / credit ring
+    uint32_t tq_head, tq_count;  // terminal_msgs ring
     // --- svr_state synthetic:100-117
     int32_t rng_svr0[4];  // stream svr_gid*3+0 (destination draws)
     int32_t rng_svr2[4];  // stream svr_gid*3+2 (codes_local_latency)
@@ -227,11 +232,9 @@ struct __attribute__((aligned(16))) NodeState {
     int32_t packet_gen, packet_fin, total_gen_size;
     int32_t vc_occupancy, terminal_length;
     uint32_t in_send_loop, issueIdle;
-    uint32_t tq_head, tq_count;  // terminal_msgs ring
     uint32_t nev;                // number of pending self events
-    uint32_t cin_head, kin_head; // records consumed from the chunk / credit ring
     uint32_t grp;        // group of `router`
-    double terminal_available_time, last_buf_full, busy_time;
+    double last_buf_full, busy_time;
     unsigned long long link_traffic, total_msg_size;
     uint32_t total_chunks, stalled_chunks, injected_chunks, ejected_chunks;
     double total_time, total_hops, max_latency, min_latency;
@@ -251,8 +254,6 @@ struct __attribute__((aligned(16))) NodeState {
     uint32_t mq_head, mq_count;  // FIFO of second-stage MN_BASE_NEW_MSG events
     double last_ts;              // key of the last executed event (causality check)
     uint32_t last_src, last_seq;
-    double self_next;            // earliest timestamp among the self-scheduled events (nev list, mq); +inf: none
-    double pad_d;
 };
 
 // scalar parameters (kernel argument, lives in the constant bank)
@@ -293,6 +294,7 @@ struct DfdParams {
     int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
     int idle_sleep_ns;                 // pause of a warp after a pass over its groups that executed nothing (0: poll again at once)
     int act_budget;                    // router events after which an activation publishes its bounds even if more would be safe
+    int prefetch;                      // an activation that gets past the poll prefetches the router's port state into L1 (partitions larger than L2)
 };
 
 struct DfdSeedConsts {  // CLCG4 constants: moduli, default seed, a^(2^(31+41)) mod m (stream jump)

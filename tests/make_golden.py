@@ -52,6 +52,7 @@ LARGE = {
     # name: (radix, links between groups, terminals, messages per terminal, routing, traffic)
     "131584_uniform_m3": (64, 2, 131584, 3, "minimal", 1),     # a=32, p=16, h=16, g=257   (~20 s of oracle time)
     "131584_par_nearest_group_m3": (64, 2, 131584, 3, "prog-adaptive", 3),  # BASELINE configs[3]: PAR, worst-case group permutation
+    "131584_par_uniform_m10": (64, 2, 131584, 10, "prog-adaptive", 1),  # bench.py's workload (parity_digest_ok)
     "1050624_uniform_m1": (128, 4, 1050624, 1, "minimal", 1),  # a=64, p=32, h=32, g=513   (~2 min, 1 GB of lp-io text)
 }
 
