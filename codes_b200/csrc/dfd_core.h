@@ -1793,57 +1793,77 @@ DFD_FN double empty_bound_k(const Ctx& c, int j) { return j < c.P->ext ? cw_boun
 // empty lanes.  Candidates are the heads of the chunk lanes, the heads of the credit lanes and the R_SEND timers;
 // an empty lane contributes its bound as a blocker {bound, 0, 0}, which beats an event of the same timestamp.
 // Every lane scans its share of the 3*radix entries, a warp argmin picks, lane 0 executes.
+// Timestamps are non-negative doubles, so a key orders like the integer pair (timestamp bits, src << 32 | seq).
+DFD_FN void key_min_at(unsigned long long& bh, unsigned long long& bl, int& bidx, const Key* p, int idx) {
+    const int4 v = *(const int4*)p;
+    const unsigned long long h = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+    const unsigned long long l = ((unsigned long long)(unsigned)v.z << 32) | (unsigned)v.w;
+    if (h < bh || (h == bh && l < bl)) {
+        bh = h;
+        bl = l;
+        bidx = idx;
+    }
+}
+
+// What an activation needs to know about the router once nothing more of it can be executed: the earliest pending event
+// (ev_min), the router's clock (a lower bound on its next event) and whether anything is pending at all.
+// `hard`: the minimum without the bounds of empty TERMINAL lanes.  Those bounds are derived from the router's own clock
+// and would let it creep upwards round by round; the next router event, however, can only come from a pending router
+// event, an external lane, or an event pending at one of the terminals.
+DFD_FN void router_horizon(Ctx& c, double best_ts) {
+    const DfdParams& P = *c.P;
+    double hard = DFD_TS_BIG;  // bounds of the empty EXTERNAL lanes
+    double evm = DFD_TS_BIG;   // pending events: heads of the non-empty lanes, R_SEND timers
+    LANE_FOR(j, P.radix) {
+        const LaneCtl L = c.lane[j];
+        const bool ext = j < P.ext;
+        double t = c.ckey[j].ts;
+        if (L.chead != L.ctail)
+            evm = mind(evm, t);
+        else if (ext)
+            hard = mind(hard, t);
+        t = c.kkey[j].ts;
+        if (L.khead != L.ktail)
+            evm = mind(evm, t);
+        else if (ext)
+            hard = mind(hard, t);
+        evm = mind(evm, c.skey[j].ts);
+    }
+    c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
+    hard = mind(warp_min_d(hard), c.ev_min);
+    c.rclock = maxd(best_ts, mind(hard, DFD_TS_BIG));
+    c.nothing_pending = !(hard < DFD_TS_BIG);
+}
+
 DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const int radix = P.radix;
     unsigned nproc = 0;
     for (;;) {
-        Key best = mk_key(DFD_TS_BIG, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        // pick: the smallest key among the 3*radix entries (every lane scans its share, a warp argmin settles it)
+        unsigned long long bh = d2bits(DFD_TS_BIG), bl = ~0ULL;
         int bidx = 3 * radix;
-        // `hard`: the same minimum without the bounds of empty TERMINAL lanes.  Those bounds are derived from the
-        // router's own clock and would let it creep upwards round by round; the next router event, however, can only
-        // come from a pending router event, an external lane, or an event pending at one of the terminals.
-        double hard = DFD_TS_BIG;  // bounds of the empty EXTERNAL lanes
-        double evm = DFD_TS_BIG;   // pending events: heads of the non-empty lanes, R_SEND timers
         LANE_FOR(j, radix) {
-            const LaneCtl L = c.lane[j];
-            const bool ext = j < P.ext;
-            Key k = c.ckey[j];
-            if (key_lt(k, best)) {
-                best = k;
-                bidx = j;
-            }
-            if (L.chead != L.ctail)
-                evm = mind(evm, k.ts);
-            else if (ext)
-                hard = mind(hard, k.ts);
-            k = c.kkey[j];
-            if (key_lt(k, best)) {
-                best = k;
-                bidx = radix + j;
-            }
-            if (L.khead != L.ktail)
-                evm = mind(evm, k.ts);
-            else if (ext)
-                hard = mind(hard, k.ts);
-            k = c.skey[j];
-            if (key_lt(k, best)) {
-                best = k;
-                bidx = 2 * radix + j;
-            }
-            evm = mind(evm, k.ts);
+            key_min_at(bh, bl, bidx, &c.ckey[j], j);
+            key_min_at(bh, bl, bidx, &c.kkey[j], radix + j);
+            key_min_at(bh, bl, bidx, &c.skey[j], 2 * radix + j);
         }
+        Key best = mk_key(bits2d(bh), (unsigned)(bl >> 32), (unsigned)bl);
         warp_argmin_key(best, bidx);
-        c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
-        hard = mind(warp_min_d(hard), c.ev_min);
-        c.rclock = maxd(best.ts, mind(hard, DFD_TS_BIG));
-        c.nothing_pending = !(hard < DFD_TS_BIG);
-        if (bidx >= 3 * radix) break;
-        int kind = bidx / radix, j = bidx - kind * radix;
-        LaneCtl L = c.lane[j];
-        bool is_event = kind == 2 || (kind == 0 ? L.chead != L.ctail : L.khead != L.ktail);
-        if (!is_event || nproc >= budget) break;
+        int kind = 0, j = 0;
+        LaneCtl L;
+        bool is_event = false;
+        if (bidx < 3 * radix) {
+            kind = bidx / radix;
+            j = bidx - kind * radix;
+            L = c.lane[j];
+            is_event = kind == 2 || (kind == 0 ? L.chead != L.ctail : L.khead != L.ktail);
+        }
+        if (!is_event || nproc >= budget) {
+            router_horizon(c, best.ts);
+            break;
+        }
         if (IS_LANE0()) {
             const double now = best.ts;
             c.h = hd;
