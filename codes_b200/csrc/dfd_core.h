@@ -1298,7 +1298,8 @@ DFD_FN int best_from_k2(const DfdParams& P, const DfdArrays& A, Ctx& R, const Ca
     long long n = cd.n;
     long long s1 = r_integer(R, 0, n - 1);
     long long off = r_integer(R, 1, n - 1);
-    long long s2 = (s1 + off) % n;
+    long long s2 = s1 + off;  // (s1 + off) % n with s1, off < n
+    if (s2 >= n) s2 -= n;
     int p1 = cand_port(P, A, R, cd, (int)s1), p2 = cand_port(P, A, R, cd, (int)s2);
     int sc1 = score_port(P, R, p1, false), sc2 = score_port(P, R, p2, false);
     // best of the two polled connections; ties broken by one more draw (always drawn: size == 2)
@@ -1835,7 +1836,10 @@ DFD_FN void router_horizon(Ctx& c, double best_ts) {
     c.nothing_pending = !(hard < DFD_TS_BIG);
 }
 
-DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
+// SPLIT: the horizon (router_horizon) is computed by a pass of its own when the phase ends -- fewer instructions per
+// event, the right trade where instruction supply bounds the run (several groups per warp); otherwise every pick scan
+// folds it in -- one pass less on the critical path of a latency-bound run (one group per warp).
+template <bool SPLIT> DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const int radix = P.radix;
@@ -1844,24 +1848,53 @@ DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsigned budget) {
         // pick: the smallest key among the 3*radix entries (every lane scans its share, a warp argmin settles it)
         unsigned long long bh = d2bits(DFD_TS_BIG), bl = ~0ULL;
         int bidx = 3 * radix;
-        LANE_FOR(j, radix) {
-            key_min_at(bh, bl, bidx, &c.ckey[j], j);
-            key_min_at(bh, bl, bidx, &c.kkey[j], radix + j);
-            key_min_at(bh, bl, bidx, &c.skey[j], 2 * radix + j);
+        double hard = DFD_TS_BIG;
+        if (SPLIT) {
+            LANE_FOR(j, radix) {
+                key_min_at(bh, bl, bidx, &c.ckey[j], j);
+                key_min_at(bh, bl, bidx, &c.kkey[j], radix + j);
+                key_min_at(bh, bl, bidx, &c.skey[j], 2 * radix + j);
+            }
+        } else {
+            double evm = DFD_TS_BIG;  // as in router_horizon
+            LANE_FOR(j, radix) {
+                const LaneCtl L = c.lane[j];
+                const bool ext = j < P.ext;
+                key_min_at(bh, bl, bidx, &c.ckey[j], j);
+                key_min_at(bh, bl, bidx, &c.kkey[j], radix + j);
+                key_min_at(bh, bl, bidx, &c.skey[j], 2 * radix + j);
+                double t = c.ckey[j].ts;
+                if (L.chead != L.ctail)
+                    evm = mind(evm, t);
+                else if (ext)
+                    hard = mind(hard, t);
+                t = c.kkey[j].ts;
+                if (L.khead != L.ktail)
+                    evm = mind(evm, t);
+                else if (ext)
+                    hard = mind(hard, t);
+                evm = mind(evm, c.skey[j].ts);
+            }
+            c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
+            hard = mind(warp_min_d(hard), c.ev_min);
         }
         Key best = mk_key(bits2d(bh), (unsigned)(bl >> 32), (unsigned)bl);
         warp_argmin_key(best, bidx);
+        if (!SPLIT) {
+            c.rclock = maxd(best.ts, mind(hard, DFD_TS_BIG));
+            c.nothing_pending = !(hard < DFD_TS_BIG);
+        }
         int kind = 0, j = 0;
         LaneCtl L;
         bool is_event = false;
         if (bidx < 3 * radix) {
-            kind = bidx / radix;
+            kind = bidx >= 2 * radix ? 2 : bidx >= radix ? 1 : 0;
             j = bidx - kind * radix;
             L = c.lane[j];
             is_event = kind == 2 || (kind == 0 ? L.chead != L.ctail : L.khead != L.ktail);
         }
         if (!is_event || nproc >= budget) {
-            router_horizon(c, best.ts);
+            if (SPLIT) router_horizon(c, best.ts);
             break;
         }
         if (IS_LANE0()) {
@@ -1967,7 +2000,7 @@ DFD_FN bool node_has_work(const Ctx& c, unsigned nl, const NodeState* ns, const 
 }
 
 // One activation of group rl.  Returns the number of events executed (0 when nothing was safe).
-DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
+template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
     const DfdParams& P = *c.P;
     const DfdArrays& A = *c.A;
     const DfdPeers& X = *c.X;
@@ -2081,7 +2114,7 @@ DFD_FN ActResult group_activate(Ctx& c, unsigned rl) {
         t1 = CYC_NOW();
         c.cyc[1] += t1 - t0;
         t0 = t1;
-        unsigned nr = router_phase(c, &hd, (unsigned)P.act_budget - nrouter);
+        unsigned nr = router_phase<SPLIT>(c, &hd, (unsigned)P.act_budget - nrouter);
         nrouter += nr;
         WARP_SYNC();
         t1 = CYC_NOW();

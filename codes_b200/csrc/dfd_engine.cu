@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
         const unsigned long long err = ld_strong64(&A.ctrl->error), done = ld_strong64(&A.ctrl->done);
         unsigned nexec = 0;
         for (unsigned g = w; g < ngroups; g += nw) {
-            ActResult a = group_activate(c, g);
+            ActResult a = group_activate<false>(c, g);
             t.n_act += a.polled_change ? 1 : 0;
             t.n_prod += a.nexec ? 1 : 0;
             nexec += a.nexec;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dfd_run_kernel_pool(DfdParams P
             i = __shfl_sync(0xFFFFFFFFu, i, 0);
             if (i == 0xFFFFFFFFu) continue;
             __threadfence_block();
-            ActResult a = group_activate(c, g0 + i);
+            ActResult a = group_activate<true>(c, g0 + i);
             __threadfence_block();
             __syncwarp();
             if (lane == 0) atomicExch_block(&s_lock[i], 0u);

@@ -291,6 +291,9 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t) {
     unsigned long long barren = 0, barren_limit = 2000000;
     if (const char* ev = getenv("DFD_CPUSIM_BARREN")) barren_limit = strtoull(ev, nullptr, 10);
     const bool sync_rounds = getenv("DFD_CPUSIM_SYNC") && atoi(getenv("DFD_CPUSIM_SYNC"));
+    // which instantiation of the activation runs: the pooled kernel's (router horizon in a pass of its own) or the
+    // one-warp-per-block kernels' (folded into every pick scan); by default the seed decides, so the suite covers both
+    const bool split_horizon = getenv("DFD_CPUSIM_SPLIT") ? atoi(getenv("DFD_CPUSIM_SPLIT")) != 0 : (seed & 1u) != 0;
     std::vector<std::pair<unsigned long long*, unsigned long long>> deferred;
     unsigned long long rounds = 0;
     for (;;) {
@@ -314,7 +317,7 @@ int dfd_device_run(DfdDevice* dev, cudaStream_t) {
             c.X = &R.X;
             c.ev = &evcount[(size_t)wp.rank * EV_NTYPES];
             for (unsigned g : wp.groups) {
-                ActResult a = group_activate(c, g);
+                ActResult a = split_horizon ? group_activate<true>(c, g) : group_activate<false>(c, g);
                 if (a.polled_change) {
                     any = true;
                     activations++;
