@@ -12,7 +12,7 @@ import json
 try:
     l=[x for x in open("gpurun_out/scale_n$n.json") if x.startswith("{")][-1]
     d=json.loads(l)
-    print("N=$n value %.1f Mev/s  e2e %.1f Mev/s  ms/step %.1f  grid %s  act/step %d" % (d["value"]/1e6, d["e2e"]["value"]/1e6, d["ms_per_step"], d["config"]["grid"], d["config"]["activations_per_step"]))
+    print("N=$n value %.1f Mev/s  e2e %.1f Mev/s  ms/step %.1f  grid %s  act/step %d  digest %s" % (d["value"]/1e6, d["e2e"]["value"]/1e6, d["ms_per_step"], d["config"]["grid"], d["config"]["activations_per_step"], d.get("parity_digest_ok")))
 except Exception as ex:
     print("N=$n failed", ex)
 PY

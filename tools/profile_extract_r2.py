@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "gpurun_out")
 DST = os.path.join(ROOT, "profiles")
 stem = sys.argv[1] if len(sys.argv) > 1 else "r2_eventloop_131k"
-workload = sys.argv[2] if len(sys.argv) > 2 else "131,584 terminals, PAR, uniform, 2 msgs/terminal (bench network, fewer messages)"
+workload = sys.argv[2] if len(sys.argv) > 2 else "131,584 terminals, PAR, uniform, 10 msgs/terminal: the bench.py workload (30,490,527 events per launch)"
 
 KEEP = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "l1tex__t_sector_hit_rate.pct", "launch__block_size",
         "launch__grid_size", "launch__registers_per_thread", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max",
@@ -18,6 +18,9 @@ KEEP = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
         "sm__icc_request_hit_rate.pct", "sm__icc_requests.sum.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum",
+        "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
         "gcc__cache_requests_type_instruction.sum", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
         "gcc__average_cache_request_hit_rate.pct"]
 
@@ -42,8 +45,8 @@ open(os.path.join(DST, stem + "_details.txt"), "w").write(det)
 rd = to_bytes(m["dram__bytes_read.sum"]["value"], m["dram__bytes_read.sum"]["unit"])
 wr = to_bytes(m["dram__bytes_write.sum"]["value"], m["dram__bytes_write.sum"]["unit"])
 print(stem, "dram bytes per launch:", int(rd + wr), "duration", m["gpu__time_duration.sum"])
-if stem.endswith("_m10"):
-    json.dump({"kernel": "dfd_run_kernel<16>", "workload": workload, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
+if stem == "r2_eventloop_131k":
+    json.dump({"kernel": "dfd_run_kernel_pool<16>", "workload": workload, "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                "dram_bytes_per_launch": int(rd + wr), "source": f"ncu --set full --clock-control none, one launch, profiles/{stem}_metrics.json"},
               open(os.path.join(DST, "r2_traffic.json"), "w"), indent=1)
 p = os.path.join(SRC, "r2_launches.csv")
