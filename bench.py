@@ -330,10 +330,12 @@ def main():
                          "frac": ach / (peak * world), "traffic": measured_traffic() if world == 1 else None,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(hops, chunks) // (world if sharded else 1),
                          "peak_source": peak_src, "kernel": "dfd_run_kernel (one launch per step per GPU)",
-                         "note": "memory-latency-bound: one warp per router group walks dependent loads of LP state (DESIGN.md 5)"},
+                         "note": "instruction-supply- and latency-bound, not bandwidth-bound: one warp per router group executes branchy event handlers "
+                                 "(GPC instruction cache at 95 % of its request rate, DRAM at 8 %; DESIGN.md 5, profiles/r2_summary.md)"},
             "e2e": {"value": events_per_step * args.steps * jobs / e2e_s, "unit": "events/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": 2 * args.steps * world, "clocks": clocks,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps, "gpu_launches_per_step": 2 * world},
+            # inside the device-timed region: one dfd_run_kernel* launch per step and GPU (the e2e region adds dfd_init_kernel)
+            "gpu_launches": args.steps * world, "clocks": clocks,
             # every lp-io file of the (merged) result hashes to the CPU oracle's digest for this workload
             "parity_digest_ok": digest_ok}
     if world == 1 and not args.no_extras:

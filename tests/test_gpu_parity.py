@@ -180,10 +180,27 @@ NARROW_CASES = [
 
 @pytest.mark.parametrize("name,conf,opts", NARROW_CASES, ids=[c[0] for c in NARROW_CASES])
 def test_large_partition_kernel_matches_oracle(tmp_path, monkeypatch, name, conf, opts):
-    """The window kernel exists in two register budgets; partitions of more than 12,288 LPs get the 128-register
-    instantiation (16 resident warps per SM).  Force it on the small configs the oracle can follow."""
+    """The one-warp-per-block event loop exists in two register budgets; partitions of more than 1,184 groups get the
+    128-register instantiation (16 resident warps per SM).  Force it on the small configs the oracle can follow."""
     monkeypatch.setenv("DFD_WIDE_REGS", "0")
     s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert_identical(s, o, g, r)
+
+
+POOL_CASES = NARROW_CASES + [
+    ("72-multichunk", CONF72, dict(num_messages=5, payload_sz=10000)),
+    ("8320-par-uniform", CONF8K, dict(num_messages=3)),
+]
+
+
+@pytest.mark.parametrize("name,conf,opts", POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_pooled_kernel_matches_oracle(tmp_path, monkeypatch, name, conf, opts):
+    """Partitions with more groups than resident warps run dfd_run_kernel_pool (16-warp blocks, groups dealt out by ticket,
+    the router horizon in a pass of its own).  Force it on the small configs the oracle can follow: the warps of a block then
+    compete for few groups, which exercises the per-group locks far harder than a large network does."""
+    monkeypatch.setenv("DFD_POOL", "1")
+    s, o, g, r = run_both(tmp_path, conf, **opts)
+    assert s.block_threads == 512
     assert_identical(s, o, g, r)
 
 
