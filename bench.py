@@ -16,7 +16,10 @@ kernel runs to completion.
              (N>1: + merge of the ranks' partitions on rank 0)
   roofline   algorithmic bytes (832*sum(N_hop) + 896*N_chunks per run) / kernel time vs the
              measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  worst_case (N=1, extra) the same network under the worst-case group permutation (configs[3]'s traffic)
+  other_configs (N=1, extra) the other BASELINE configurations on the same GPU, device-timed like `value`: configs[1] (1,056
+             terminals, minimal), configs[2] (8,320 terminals, PAR; uniform and nearest-group), configs[3] (the bench network
+             under the worst-case group permutation, also as `worst_case`); configs[1] and configs[2] with the reference's own
+             sources (oracle/_ref, kind "reference", 1 core) timed beside them
   cpu_baseline  (N=1) the CPU implementation of the path, single thread, on a bounded sample of the workload (1 message
              per terminal, 3.1 M events).  At this size that is the restatement oracle (kind "port"): oracle/_ref, the
              reference's own sources on the sequential shim engine, needs more than 15 minutes to set this network up.
@@ -210,7 +213,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the worst-case-permutation figure (N=1 only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the figures for the other BASELINE configurations (N=1 only)")
     ap.add_argument("--replicas", action="store_true", help="N>1: run N independent replicas instead of the group-sharded engine")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -339,18 +342,44 @@ def main():
             # every lp-io file of the (merged) result hashes to the CPU oracle's digest for this workload
             "parity_digest_ok": digest_ok}
     if world == 1 and not args.no_extras:
-        try:  # not the headline: the same network under the worst-case group permutation (BASELINE configs[3]'s traffic)
-            e2 = codes_b200.Engine()
-            e2.setup(conf, codes_b200.make_opts(**dict(w, traffic=3)))
-            e2.upload(stream)
-            ms = device_timed(e2, stream, flush, fence, False, 3, 1)
-            e2.finish(stream)
-            s2 = e2.summary()
-            e2.close()
-            line["worst_case"] = {"workload": "same network and routing, nearest-group (worst-case group permutation) traffic",
-                                  "value": 3 * s2.events / (ms * 1e-3), "unit": "events/s", "events_per_step": s2.events, "steps": 3}
-        except Exception as ex:  # the extra figure must never cost the headline
-            line["worst_case"] = {"error": repr(ex)[:200]}
+        # Not the headline: the other BASELINE configurations on the same GPU, device-timed like `value` (1 warm-up + 3
+        # timed runs each, L2 flushed in between), each with its own roofline fraction on algorithmic bytes.
+        def extra(name, conf_path, workload_text, cpu_ref=False, **kw):
+            try:
+                e2 = codes_b200.Engine()
+                e2.setup(conf_path, codes_b200.make_opts(**kw))
+                e2.upload(stream)
+                ms = device_timed(e2, stream, flush, fence, False, 3, 1)
+                e2.finish(stream)
+                s2 = e2.summary()
+                e2.close()
+                bps = algorithmic_bytes(s2.total_hops, s2.finished_chunks) * 3 / (ms * 1e-3) / 1e9
+                out = {"workload": workload_text, "value": 3 * s2.events / (ms * 1e-3), "unit": "events/s",
+                       "events_per_step": s2.events, "steps": 3, "ms_per_step": ms / 3, "grid": [s2.grid_blocks, s2.block_threads],
+                       "roofline_frac": bps / peak, "achieved_gbs": bps}
+                if cpu_ref and not args.no_cpu_baseline:
+                    from tests import oracle_util
+                    if oracle_util.ref_available():  # the reference's own sources on the sequential shim engine, 1 core
+                        ev, secs, _ = oracle_util.run_ref(conf_path, os.path.join(tmpdir.name, "ref_" + name), **kw)
+                        out["cpu_reference"] = {"value": ev / secs, "unit": "events/s", "cores": 1, "kind": "reference",
+                                                "events_identical": ev == s2.events}
+                line.setdefault("other_configs", {})[name] = out
+            except Exception as ex:  # an extra figure must never cost the headline
+                line.setdefault("other_configs", {})[name] = {"error": repr(ex)[:200]}
+
+        cdir = os.path.join(ROOT, "configs")
+        extra("configs1_1056_minimal_uniform", os.path.join(cdir, "dfdally-1056.conf"),
+              "BASELINE configs[1]: 1,056 terminals, minimal routing, uniform, 100 msgs/terminal", cpu_ref=True, traffic=1, num_messages=100)
+        extra("configs2_8320_par_uniform", os.path.join(cdir, "dfdally-8320-par.conf"),
+              "BASELINE configs[2] network: 8,320 terminals, PAR, uniform, 20 msgs/terminal", cpu_ref=True, traffic=1, num_messages=20)
+        extra("configs2_8320_par_nearest_group", os.path.join(cdir, "dfdally-8320-par.conf"),
+              "same network, nearest-group (worst-case group permutation) traffic", traffic=3, num_messages=20)
+        extra("configs3_131584_par_nearest_group", conf,
+              "BASELINE configs[3]: the bench network under the worst-case group permutation", **dict(w, traffic=3))
+        if "value" in line["other_configs"].get("configs3_131584_par_nearest_group", {}):
+            wc = line["other_configs"]["configs3_131584_par_nearest_group"]
+            line["worst_case"] = {"workload": wc["workload"], "value": wc["value"], "unit": "events/s",
+                                  "events_per_step": wc["events_per_step"], "steps": 3}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the CPU baseline is timed at N=1 only
         ev, pk, secs, kind = cpu_sample(conf)
         line["cpu_baseline"] = {"value": ev / secs, "unit": "events/s", "cores": 1, "kind": kind,
