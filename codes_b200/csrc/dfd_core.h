@@ -2077,7 +2077,8 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
     c.wrote_remote = false;
     RouterHdr hd = A.rh[rl];  // lane 0's working copy; written back once
     WARP_SYNC();
-    long long t0 = CYC_NOW(), t1;
+    // phase cycle accounting: only in the one-warp-per-block kernels (the pooled kernel is short of registers)
+    long long t0 = SPLIT ? 0LL : CYC_NOW(), t1;
     // ---- (2) rounds of router phase + node phase until nothing more is safe (or the event budget is spent)
     c.gid = hd.gid;
     c.lid = hd.lid;
@@ -2089,10 +2090,12 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
     bool more = false;
     for (;;) {
         const double clock_in = c.rclock;
-        c.nrounds++;
-        t1 = CYC_NOW();
-        c.cyc[0] += t1 - t0;
-        t0 = t1;
+        if (!SPLIT) c.nrounds++;
+        if (!SPLIT) {
+            t1 = CYC_NOW();
+            c.cyc[0] += t1 - t0;
+            t0 = t1;
+        }
         // bounds of the terminal lanes as seen by the router
         bool nwork = false;
         double nfloor = DFD_TS_BIG;
@@ -2111,15 +2114,19 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
         c.node_floor = warp_min_d(nfloor);
         c.node_push_min = DFD_TS_BIG;
         WARP_SYNC();
-        t1 = CYC_NOW();
-        c.cyc[1] += t1 - t0;
-        t0 = t1;
+        if (!SPLIT) {
+            t1 = CYC_NOW();
+            c.cyc[1] += t1 - t0;
+            t0 = t1;
+        }
         unsigned nr = router_phase<SPLIT>(c, &hd, (unsigned)P.act_budget - nrouter);
         nrouter += nr;
         WARP_SYNC();
-        t1 = CYC_NOW();
-        c.cyc[2] += t1 - t0;
-        t0 = t1;
+        if (!SPLIT) {
+            t1 = CYC_NOW();
+            c.cyc[2] += t1 - t0;
+            t0 = t1;
+        }
         unsigned nn = 0;
         // the router phase can only raise a terminal's horizon or hand it new records: without router events the
         // terminals that had nothing to do before it still have nothing to do
@@ -2135,9 +2142,11 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
         if (IS_LANE0()) c.nexec += nr;
         nn = warp_sum_u(nn);
         total += nr + nn;
-        t1 = CYC_NOW();
-        c.cyc[3] += t1 - t0;
-        t0 = t1;
+        if (!SPLIT) {
+            t1 = CYC_NOW();
+            c.cyc[3] += t1 - t0;
+            t0 = t1;
+        }
 #ifdef DFD_DEBUG_HOST
         {
             static unsigned long long dbg_rounds = 0;
@@ -2245,7 +2254,9 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
             }
         }
     }
-    t1 = CYC_NOW();
-    c.cyc[4] += t1 - t0;
+    if (!SPLIT) {
+        t1 = CYC_NOW();
+        c.cyc[4] += t1 - t0;
+    }
     return res;
 }
