@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dfd_run_kernel_pool(DfdParams P
         for (unsigned k = 0; k < per_pass; k++) {
             unsigned i = 0;
             if (lane == 0) {
-                i = atomicAdd(&s_ticket, 1u) % ng;
+                i = atomicInc(&s_ticket, ng - 1);  // round-robin over the block's groups, wraps at ng
                 if (atomicExch_block(&s_lock[i], 1u) != 0u) i = 0xFFFFFFFFu;  // another warp is on it
             }
             i = __shfl_sync(0xFFFFFFFFu, i, 0);
