@@ -21,7 +21,7 @@ DFD_FN void seed_stream(int32_t* s, unsigned long long stream, const DfdSeedCons
 DFD_FN void init_ctrl(const DfdParams& P, const DfdArrays& A, const DfdPeers& X) {
     (void)P;
     memset(A.ctrl, 0, sizeof(DfdCtrl));
-    A.ctrl->created = (unsigned long long)(X.n1 - X.n0);  // one KICKOFF per server
+    A.ctrl->created = 0.0 + P.mean_interval < P.ts_end ? (unsigned long long)(X.n1 - X.n0) : 0ULL;  // one KICKOFF per server
     for (int i = 0; i < 64; i++) A.counters[i] = 0;
 }
 
@@ -50,6 +50,10 @@ DFD_FN void init_node(const DfdParams& P, const DfdArrays& A, const DfdPeers& X,
     s->nev = 1;
     s->nev_hwm = 1;
     s->self_next = ev->ts;
+    if (!(ev->ts < P.ts_end)) {  // the run ends before the first KICKOFF (--end below the inter-arrival time): never sent
+        s->nev = 0;
+        s->self_next = DINF;
+    }
     A.ncin_tail[nl] = 0;
     A.nkin_tail[nl] = 0;
     A.ack_count[nl] = 0;

@@ -70,3 +70,10 @@ def test_long_burst_of_messages(tmp_path):
     self-event list of 24 could hold); they now live in their own FIFO sized by num_messages."""
     check(tmp_path, CONF72, seed=11, world=1, num_messages=60, arrival_time=1.0)
     check(tmp_path, CONF72, seed=12, world=1, num_messages=40, payload_sz=8, load_per_svr=0.5)
+
+
+def test_run_ends_before_the_first_kickoff(tmp_path):
+    """Found by the round-2 random campaign on the GPU (3 of 300 cases): --end below the inter-arrival time means the first
+    KICKOFF of every server is never sent; the engine used to execute it."""
+    check(tmp_path, CONF72, seed=13, world=1, num_messages=2, arrival_time=5000.0, end_time=4000.0)
+    check(tmp_path, CONF72, seed=14, world=2, num_messages=2, arrival_time=5000.0, end_time=4000.0)

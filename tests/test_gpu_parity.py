@@ -57,7 +57,8 @@ CASES = [
     ("72-burst", CONF72, dict(num_messages=1, arrival_time=1.0)),
     ("72-long-burst", CONF72, dict(num_messages=40, arrival_time=1.0)),  # inter-arrival below nic_seq_delay: queued NEW_MSG events pile up
     ("72-long-burst-tiny", CONF72, dict(num_messages=40, payload_sz=8, load_per_svr=0.5)),
-    ("72-early-end", CONF72, dict(num_messages=3, end_time=1500.0)),    # the run ends before the first packet arrives
+    ("72-early-end", CONF72, dict(num_messages=3, end_time=1500.0)),
+    ("72-end-before-first-kickoff", CONF72, dict(num_messages=2, arrival_time=5000.0, end_time=4000.0)),  # nothing ever runs    # the run ends before the first packet arrives
     ("1056-uniform", CONF1056, dict(num_messages=10)),
     ("1056-nearest-group", CONF1056, dict(num_messages=5, traffic=3)),
     ("8320-par-uniform", CONF8K, dict(num_messages=3)),
