@@ -1787,6 +1787,32 @@ DFD_FN_NOINLINE void router_buf_update(Ctx& R, double now, int indx, int output_
 }
 
 // bound of an empty lane: from the channel word of an external lane, from iblk for a terminal lane
+// R_SNAPSHOT (PARAMS router_buffer_snapshots): router_send_snapshot_events dally:4363-4417 sends every router one self event
+// per configured timestamp at init; here they are a cursor (RouterHdr::snap_next) into the time-sorted list.  The key of
+// the pending one is (time, router gid, configured index): the index is the sequence number the event got at init.
+// Read from the group's header in memory so that a run without snapshots (P.nsnap == 0, the common case) pays one
+// uniform branch and no register.
+DFD_FN bool snap_pending(const Ctx& c, Key* k) {
+    const unsigned i = c.A->rh[c.rl].snap_next;
+    if (i >= (unsigned)c.P->nsnap) return false;
+    *k = mk_key(c.A->snap_ts[i], c.gid, c.A->snap_id[i]);
+    return true;
+}
+DFD_FN double snap_next_ts(const Ctx& c) {
+    const unsigned i = c.A->rh[c.rl].snap_next;
+    return i < (unsigned)c.P->nsnap ? c.A->snap_ts[i] : DFD_TS_BIG;
+}
+// router_handle_snapshot_event dally:4419-4437: vc_occupancy[port][vc] of every port into snapshot_data[packet_ID]
+DFD_FN_NOINLINE void router_snapshot(Ctx& c, RouterHdr* hd) {
+    const DfdParams& P = *c.P;
+    const DfdArrays& A = *c.A;
+    const unsigned i = hd->snap_next;
+    int4* dst = A.snap + ((size_t)c.rl * P.nsnap_all + A.snap_id[i]) * P.radix;
+    for (int j = 0; j < P.radix; j++) dst[j] = *(const int4*)c.port[j].vc_occ;
+    hd->snap_next = i + 1;
+    A.rh[c.rl].snap_next = i + 1;  // what the other lanes (and the next pick) read
+}
+
 DFD_FN double empty_bound_c(const Ctx& c, int j) { return j < c.P->ext ? cw_bound(c.seen_c[j]) : c.iblk[j - c.P->ext]; }
 DFD_FN double empty_bound_k(const Ctx& c, int j) { return j < c.P->ext ? cw_bound(c.seen_k[j]) : c.iblk[c.P->p + (j - c.P->ext)]; }
 
@@ -1830,6 +1856,7 @@ DFD_FN void router_horizon(Ctx& c, double best_ts) {
             hard = mind(hard, t);
         evm = mind(evm, c.skey[j].ts);
     }
+    if (P.nsnap) evm = mind(evm, snap_next_ts(c));
     c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
     hard = mind(warp_min_d(hard), c.ev_min);
     c.rclock = maxd(best_ts, mind(hard, DFD_TS_BIG));
@@ -1875,19 +1902,31 @@ template <bool SPLIT> DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsign
                     hard = mind(hard, t);
                 evm = mind(evm, c.skey[j].ts);
             }
+            if (P.nsnap) evm = mind(evm, snap_next_ts(c));
             c.ev_min = mind(warp_min_d(mind(evm, c.node_push_min)), c.node_floor);
             hard = mind(warp_min_d(hard), c.ev_min);
         }
         Key best = mk_key(bits2d(bh), (unsigned)(bl >> 32), (unsigned)bl);
         warp_argmin_key(best, bidx);
+        bool snap = false;
+        if (P.nsnap) {  // the pending R_SNAPSHOT competes with the winner of the scan
+            Key sk;
+            if (snap_pending(c, &sk) && key_lt(sk, best)) {
+                best = sk;
+                snap = true;
+            }
+        }
         if (!SPLIT) {
             c.rclock = maxd(best.ts, mind(hard, DFD_TS_BIG));
             c.nothing_pending = !(hard < DFD_TS_BIG);
         }
         int kind = 0, j = 0;
-        LaneCtl L;
+        LaneCtl L = LaneCtl();
         bool is_event = false;
-        if (bidx < 3 * radix) {
+        if (snap) {
+            kind = 3;
+            is_event = true;
+        } else if (bidx < 3 * radix) {
             kind = bidx >= 2 * radix ? 2 : bidx >= radix ? 1 : 0;
             j = bidx - kind * radix;
             L = c.lane[j];
@@ -1900,8 +1939,11 @@ template <bool SPLIT> DFD_FN unsigned router_phase(Ctx& c, RouterHdr* hd, unsign
         if (IS_LANE0()) {
             const double now = best.ts;
             c.h = hd;
-            check_order(c, &hd->last_ts, &hd->last_src, &hd->last_seq, best.ts, best.src, best.seq, kind != 2, c.r);
-                if (kind == 0) {
+            check_order(c, &hd->last_ts, &hd->last_src, &hd->last_seq, best.ts, best.src, best.seq, kind < 2, c.r);
+            if (kind == 3) {
+                count_ev(c.ev, EV_R_SNAPSHOT);
+                router_snapshot(c, hd);
+            } else if (kind == 0) {
                 ChunkRec rec;
                 const ChunkRec* src = c.ring_c + ring_c_idx(A, j, L.chead);
 #pragma unroll

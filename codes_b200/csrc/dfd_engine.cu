@@ -389,6 +389,8 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     off = align256(off + NRX * radix * sizeof(PortState));
     size_t o_cnt = off;
     off = align256(off + 64 * sizeof(unsigned long long));
+    size_t o_snap = off;
+    off = align256(off + NRX * (size_t)P.nsnap_all * radix * sizeof(int4));
     char* xr = nullptr;
     if (dalloc(dev, &xr, off)) return 1;
     dev->xregion = xr;
@@ -399,6 +401,15 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     A.rh = (RouterHdr*)(xr + o_rh);
     A.port = (PortState*)(xr + o_port);
     A.counters = (unsigned long long*)(xr + o_cnt);
+    A.snap = (int4*)(xr + o_snap);
+    {
+        double* d = nullptr;
+        unsigned* u = nullptr;
+        if (dalloc(dev, &d, (size_t)P.nsnap_all)) return 1;
+        if (dalloc(dev, &u, (size_t)P.nsnap_all)) return 1;
+        A.snap_ts = d;
+        A.snap_id = u;
+    }
     A.ctrl = (DfdCtrl*)xr;
     A.cw_c = (unsigned long long*)(xr + o_cwc);
     A.cw_k = (unsigned long long*)(xr + o_cwk);
@@ -526,6 +537,15 @@ int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t st
         if (!tabs[i]->empty()) CK(cudaMemcpyAsync((void*)dst[i], tabs[i]->data(), tabs[i]->size() * sizeof(int), cudaMemcpyHostToDevice, st));
         total += tabs[i]->size() * sizeof(int);
     }
+    if ((int)T.snap_ts.size() != dev->P.nsnap || dev->P.nsnap > dev->P.nsnap_all) {
+        snprintf(dev->error, sizeof dev->error, "snapshot schedule does not match the device parameters");
+        return 1;
+    }
+    if (dev->P.nsnap) {
+        CK(cudaMemcpyAsync((void*)A.snap_ts, T.snap_ts.data(), T.snap_ts.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync((void*)A.snap_id, T.snap_id.data(), T.snap_id.size() * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        total += T.snap_ts.size() * (sizeof(double) + sizeof(unsigned));
+    }
     dev->topo_bytes = total;
     return 0;
 }
@@ -558,6 +578,7 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st, in
     out->node.resize(P.NT);
     out->rh.resize(P.NR);
     out->port.resize((size_t)P.NR * P.radix);
+    out->snap.resize((size_t)P.NR * P.nsnap_all * P.radix);
     out->ack_count.resize(P.NT);
     out->ack_first.resize(P.NT);
     out->ack_last.resize(P.NT);
@@ -583,7 +604,11 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t st, in
             CK(cudaMemcpyAsync(out->ack_count.data() + Y.n0, at(A.ack_count), sizeof(unsigned) * nt, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(out->ack_first.data() + Y.n0, at(A.ack_first), sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(out->ack_last.data() + Y.n0, at(A.ack_last), sizeof(unsigned long long) * nt, cudaMemcpyDeviceToHost, st));
-            out->d2h_bytes += sizeof(NodeState) * nt + sizeof(RouterHdr) * nr + sizeof(PortState) * nr * P.radix + (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * nt;
+            const size_t snap_per_router = (size_t)P.nsnap_all * P.radix;
+            if (P.nsnap)
+                CK(cudaMemcpyAsync(out->snap.data() + (size_t)Y.r0 * snap_per_router, at(A.snap), sizeof(int4) * nr * snap_per_router, cudaMemcpyDeviceToHost, st));
+            out->d2h_bytes += sizeof(NodeState) * nt + sizeof(RouterHdr) * nr + sizeof(PortState) * nr * P.radix + (sizeof(unsigned) + 2 * sizeof(unsigned long long)) * nt +
+                              (P.nsnap ? sizeof(int4) * nr * snap_per_router : 0);
         }
         CK(cudaMemcpyAsync(cnt[k], at(A.counters), sizeof cnt[k], cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(&ctrl[k], at(A.ctrl), sizeof(DfdCtrl), cudaMemcpyDeviceToHost, st));

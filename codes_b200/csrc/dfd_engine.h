@@ -13,6 +13,9 @@
 
 struct DfdHostTopo {  // flattened connection tables (see DfdArrays)
     std::vector<int> loc_off, loc_port, loc_dest, lout_lane, lin_src, gs_port, gs_group, gdest, gout_lane, gin_src, gin_port, routed_off, routed_lid;
+    // R_SNAPSHOT schedule (PARAMS router_buffer_snapshots): the times before ts_end sorted by (time, configured index)
+    std::vector<double> snap_ts;
+    std::vector<unsigned> snap_id;
 };
 
 // page-locked host array (device -> host copies at full PCIe rate, no staging); grows, never shrinks
@@ -62,6 +65,7 @@ struct DfdHostResults {  // indexed by GLOBAL node / router id
     PinnedBuf<NodeState> node;
     PinnedBuf<RouterHdr> rh;
     PinnedBuf<PortState> port;
+    PinnedBuf<int4> snap;  // [NR][nsnap_all][radix] vc_occupancy captured by the R_SNAPSHOT events
     PinnedBuf<unsigned> ack_count;
     PinnedBuf<unsigned long long> ack_first, ack_last;
     unsigned long long counters[64];

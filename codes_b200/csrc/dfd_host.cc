@@ -168,6 +168,7 @@ struct HostParams {
     std::string intra_file, inter_file;
     int repetitions = 0, n_svr = 0, n_term = 0, n_rtr = 0, off_svr = 0, off_term = 0, off_rtr = 0, lps_per_rep = 0;
     std::vector<std::string> modelnet_order;
+    std::vector<double> snapshot_times;  // PARAMS router_buffer_snapshots (dally:2783-2797)
 };
 
 struct LpioFile {
@@ -372,6 +373,11 @@ int read_params(dfd_engine* e) {
     const auto* order = g.s ? g.s->find("modelnet_order") : nullptr;
     if (!order) return fail(e, "unable to read PARAMS:modelnet_order variable\n");
     p.modelnet_order = *order;
+    // router VC-occupancy snapshots: a list of timestamps, each read with strtod (dally:2783-2797)
+    p.snapshot_times.clear();
+    if (const auto* snaps = g.s ? g.s->find("router_buffer_snapshots") : nullptr)
+        for (const std::string& t : *snaps) p.snapshot_times.push_back(strtod(t.c_str(), nullptr));
+    if (p.snapshot_times.size() > 4096) return fail(e, "router_buffer_snapshots: more than 4096 snapshots are not supported by this engine");
     return 0;
 }
 
@@ -599,6 +605,31 @@ void render_lpio(dfd_engine* e) {
     const HostParams& p = e->hp;
     const dfd_synthetic_opts& o = e->opts;
     e->lpio.clear();
+    if (!p.snapshot_times.empty()) {
+        // dragonfly-snapshots.csv: router 0 writes the header at init (dally:4364-4403); every R_SNAPSHOT writes its record
+        // when it commits (dally:4687-4709), i.e. in the order of the sequential run: by (time, router gid)
+        std::string text = "#Time of snapshot,Router ID,";
+        for (int i = 0; i < p.radix; i++)
+            for (int j = 0; j < DFD_NUM_VCS; j++) text += sfmt("Port %d VC %d,", i, j);
+        text[text.size() - 1] = '\n';
+        const size_t per_router = p.snapshot_times.size() * (size_t)p.radix;
+        const std::vector<double>& sts = e->topo.snap_ts;
+        for (size_t k0 = 0; k0 < sts.size();) {  // runs of equal timestamps: (time, router gid, configured index) order
+            size_t k1 = k0;
+            while (k1 < sts.size() && sts[k1] == sts[k0]) k1++;
+            for (int r = 0; r < p.total_routers; r++)
+                for (size_t k = k0; k < k1; k++) {
+                    const unsigned id = e->topo.snap_id[k];
+                    const int4* occ = e->res.snap.data() + (size_t)r * per_router + (size_t)id * p.radix;
+                    text += sfmt("%.4f, %d, ", p.snapshot_times[id], r);
+                    for (int i = 0; i < p.radix; i++) text += sfmt("%d, %d, %d, %d, ", occ[i].x, occ[i].y, occ[i].z, occ[i].w);
+                    text.resize(text.size() - 2);
+                    text += '\n';
+                }
+            k0 = k1;
+        }
+        lpio_write(e, "dragonfly-snapshots.csv", text);
+    }
     for (int rep = 0; rep < p.repetitions; rep++) {
         for (int off = 0; off < p.lps_per_rep; off++) {
             unsigned g = (unsigned)rep * p.lps_per_rep + off;
@@ -1013,6 +1044,20 @@ static int make_device_params(dfd_engine* e, DfdParams* P) {
     P->prefetch = 0;
     if (const char* ev = getenv("DFD_ACT_BUDGET")) P->act_budget = std::max(1, atoi(ev));
     P->ts_end = o.end_time > 0 ? o.end_time : (p.end_time > 0 ? p.end_time : 5.0 * 24 * 60 * 60 * 1000.0 * 1000.0 * 1000.0);
+    {   // R_SNAPSHOT schedule: an event at or past the end of the run is never sent (tw_event_new); the others in key order
+        std::vector<std::pair<double, unsigned>> sched;
+        for (size_t i = 0; i < p.snapshot_times.size(); i++)
+            if (0.0 + p.snapshot_times[i] < P->ts_end) sched.push_back({0.0 + p.snapshot_times[i], (unsigned)i});
+        std::sort(sched.begin(), sched.end());
+        e->topo.snap_ts.clear();
+        e->topo.snap_id.clear();
+        for (const auto& s : sched) {
+            e->topo.snap_ts.push_back(s.first);
+            e->topo.snap_id.push_back(s.second);
+        }
+        P->nsnap = (int)sched.size();
+        P->nsnap_all = (int)p.snapshot_times.size();
+    }
     P->traffic = o.traffic;
     P->num_msgs = o.num_messages;
     P->payload_sz = o.payload_sz;
@@ -1137,7 +1182,7 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
         reuse = Q.NT == P.NT && Q.NR == P.NR && Q.radix == P.radix && Q.a == P.a && Q.p == P.p && Q.G == P.G && Q.h == P.h &&
                 Q.ncin_cap == P.ncin_cap && Q.nkin_cap == P.nkin_cap && Q.nsq_cap == P.nsq_cap && Q.ntq_cap == P.ntq_cap &&
                 Q.nev_cap == P.nev_cap && Q.nreasm_cap == P.nreasm_cap && Q.cap_l == P.cap_l && Q.cap_g == P.cap_g &&
-                Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap;
+                Q.cap_tc == P.cap_tc && Q.cap_tk == P.cap_tk && Q.rpool_cap == P.rpool_cap && Q.nsnap_all == P.nsnap_all;
     }
     if (reuse) {
         const int budget = e->dev.P.act_budget, idle_sleep = e->dev.P.idle_sleep_ns, prefetch = e->dev.P.prefetch;  // chosen by dfd_device_create from the grid it sized
@@ -1205,7 +1250,7 @@ static void fill_summary_meta(dfd_engine* e) {
 static void profile_print(dfd_engine* e) {
     if (!getenv("DFD_PROFILE_PRINT")) return;
     const unsigned long long* C = e->res.counters;
-    const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"};
+    const char* names[] = {"KICKOFF", "REMOTE", "LOCAL", "ACK", "NEW_MSG", "SCHED_NEXT", "T_GENERATE", "T_ARRIVE", "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER", "R_SNAPSHOT"};
     for (int i = 0; i < EV_NTYPES; i++)
         if (C[4 + i]) fprintf(stderr, "  %-11s n=%9llu\n", names[i], C[4 + i]);
     fprintf(stderr, "  warps %d, passes %llu, activations past the poll %llu, productive %llu, events/productive activation %.2f\n", e->dev.warps, C[23], C[22], C[1],
@@ -1293,7 +1338,8 @@ long long dfd_engine_partition_bytes(const dfd_engine* e) {
     const DfdPeers& X = e->dev.X;
     size_t nn = X.n1 - X.n0, nr = X.r1 - X.r0;
     return (long long)(sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) +
-                       nr * (sizeof(RouterHdr) + (size_t)e->hp.radix * sizeof(PortState)));
+                       nr * (sizeof(RouterHdr) + (size_t)e->hp.radix * sizeof(PortState)) +
+                       nr * e->hp.snapshot_times.size() * (size_t)e->hp.radix * sizeof(int4));
 }
 int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len) {
     if (!e->downloaded) return fail(e, "export_partition: engine_finish has not been called");
@@ -1325,6 +1371,7 @@ int dfd_engine_export_partition(dfd_engine* e, void* buf, long long len) {
     PUT(e->res.ack_last, X.n0, nn)
     PUT(e->res.rh, X.r0, nr)
     PUT(e->res.port, (size_t)X.r0 * radix, nr * radix)
+    PUT(e->res.snap, (size_t)X.r0 * radix * e->hp.snapshot_times.size(), nr * radix * e->hp.snapshot_times.size())
 #undef PUT
     return 0;
 }
@@ -1343,7 +1390,9 @@ int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
         if (h.n0 != Y.n0 || h.n1 != Y.n1 || h.r0 != Y.r0 || h.r1 != Y.r1) return fail(e, "import_partition: bounds do not match the partition of rank %d", h.rank);
     }
     const size_t nn = (size_t)(h.n1 - h.n0), nr = (size_t)(h.r1 - h.r0);
-    const size_t need = sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) + nr * (sizeof(RouterHdr) + radix * sizeof(PortState));
+    const size_t nsnap = e->hp.snapshot_times.size();
+    const size_t need = sizeof(PartHeader) + nn * (sizeof(NodeState) + sizeof(unsigned) + 2 * sizeof(unsigned long long)) +
+                        nr * (sizeof(RouterHdr) + radix * sizeof(PortState)) + nr * nsnap * radix * sizeof(int4);
     if ((size_t)len < need) return fail(e, "import_partition: truncated buffer (%lld bytes, need %zu)", len, need);
     if (h.counters[2]) return fail(e, "rank %d reported device error %llu (%s)", h.rank, h.counters[2], device_error_name(h.counters[2]));
     if (e->gathered) return 0;  // engine_finish has already read this partition over the peer mapping
@@ -1356,6 +1405,7 @@ int dfd_engine_import_partition(dfd_engine* e, const void* buf, long long len) {
     GET(e->res.ack_last, h.n0, nn)
     GET(e->res.rh, h.r0, nr)
     GET(e->res.port, (size_t)h.r0 * radix, nr * radix)
+    GET(e->res.snap, (size_t)h.r0 * radix * nsnap, nr * radix * nsnap)
 #undef GET
     e->res.counters[0] += h.counters[0];  // committed events
     e->res.counters[1] += h.counters[1];

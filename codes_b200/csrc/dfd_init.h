@@ -22,6 +22,7 @@ DFD_FN void init_ctrl(const DfdParams& P, const DfdArrays& A, const DfdPeers& X)
     (void)P;
     memset(A.ctrl, 0, sizeof(DfdCtrl));
     A.ctrl->created = 0.0 + P.mean_interval < P.ts_end ? (unsigned long long)(X.n1 - X.n0) : 0ULL;  // one KICKOFF per server
+    A.ctrl->created += (unsigned long long)(X.r1 - X.r0) * (unsigned long long)P.nsnap;          // R_SNAPSHOT events per router
     for (int i = 0; i < 64; i++) A.counters[i] = 0;
 }
 
@@ -76,6 +77,10 @@ DFD_FN void init_router(const DfdParams& P, const DfdArrays& A, const DfdPeers& 
     A.pollhdr[rl].flags = 2u;
     A.pollhdr[rl].pad = 0;
     h->pad1 = 0.0;
+    // router_send_snapshot_events dally:4407-4414: the router's first nsnap_all events are its R_SNAPSHOTs (sequence numbers
+    // 0..nsnap_all-1, also those past the end of the run, which are never sent)
+    h->seq = (uint32_t)P.nsnap_all;
+    h->snap_next = 0;
     for (int i = 0; i < 2 * P.p; i++) A.iblk[(size_t)rl * 2 * P.p + i] = 0.0;
 }
 

@@ -30,6 +30,7 @@ enum DfdEv {
     EV_R_SEND,
     EV_R_ARRIVE,
     EV_R_BUFFER,
+    EV_R_SNAPSHOT,  // router VC-occupancy snapshot (PARAMS router_buffer_snapshots, dally:4363-4437)
     EV_NTYPES
 };
 
@@ -152,7 +153,7 @@ struct __attribute__((aligned(16))) RouterHdr {
     uint32_t last_src, last_seq;
     unsigned long long rng_draws;
     uint32_t more;       // the last activation stopped on its event budget: safe events may remain
-    uint32_t pad0;
+    uint32_t snap_next;  // R_SNAPSHOT events executed so far = index of the next one in the time-sorted list (DfdArrays::snap_ts)
     unsigned long long activations;  // activations that executed at least one event
     double ev_min;       // earliest pending event of the group (router and terminals) when the last activation ended
     double pad1;
@@ -294,6 +295,7 @@ struct DfdParams {
     int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
     int idle_sleep_ns;                 // pause of a warp after a pass over its groups that executed nothing (0: poll again at once)
     int act_budget;                    // router events after which an activation publishes its bounds even if more would be safe
+    int nsnap, nsnap_all;              // R_SNAPSHOT events per router: those before ts_end (the ones that exist) / configured
     int prefetch;                      // an activation that gets past the poll prefetches the router's port state into L1 (partitions larger than L2)
 };
 
@@ -358,6 +360,9 @@ struct DfdArrays {
     ChunkRec* ring_c;            // [NRmax][cslots]
     Key* ring_k;                 // [NRmax][kslots]
     DfdCtrl* ctrl;
+    int4* snap;             // [NRmax][nsnap_all][radix] vc_occupancy[port][0..3] captured by R_SNAPSHOT number i (statistics: exchange region)
+    const double* snap_ts;  // [nsnap]  snapshot times before ts_end, sorted by (time, configured index)
+    const unsigned* snap_id; // [nsnap] configured index of each (= packet_ID = sequence number of the event, dally:4407-4414)
     const uint2* lgeo;      // [radix][2]  {ring offset, capacity - 1} of chunk in-lane j and of credit lane j (same for every router)
     // topology (read-only, global router ids)
     const int* loc_off;     // [a*a+1]   CSR over (my lid, dest lid) -> local ports

@@ -291,6 +291,7 @@ struct Params {
     int repetitions = 0;
     int n_svr_per_rep = 0, n_term_per_rep = 0, n_rtr_per_rep = 0;
     int off_svr = 0, off_term = 0, off_rtr = 0, lps_per_rep = 0;
+    std::vector<double> snapshot_times;  // PARAMS router_buffer_snapshots dally:2783-2797
 };
 
 std::string resolve_path(const std::string& p, const std::string& conf_dir) {
@@ -475,6 +476,10 @@ Params read_params(const ConfNode& root, const std::string& conf_dir, FILE* log)
     if (r.get_double("cn_bandwidth", &p.svr_link_bandwidth)) p.svr_link_bandwidth = 0;
     if (!p.svr_link_bandwidth) p.svr_link_bandwidth = 4.7;
 
+    // ---- router VC-occupancy snapshots dally:2783-2797: a list of timestamps, each read with strtod
+    if (r.p->kv.count("router_buffer_snapshots"))
+        for (const std::string& v : r.p->kv.at("router_buffer_snapshots")) p.snapshot_times.push_back(strtod(v.c_str(), nullptr));
+
     // consistency dally:4925-4931
     if (p.n_rtr_per_rep != 1 || p.n_term_per_rep != p.num_cn)
         die("LPGROUPS layout must be num_cns_per_router terminals and 1 router per repetition");
@@ -616,6 +621,7 @@ enum EvType : uint8_t {
     R_SEND,
     R_ARRIVE,
     R_BUFFER,
+    R_SNAPSHOT,
     N_EV_TYPES
 };
 
@@ -746,6 +752,7 @@ struct RouterState {  // router_state dally:822-888
     std::vector<int> in_send_loop, queued_count, last_qos_lvl, vc_max_sizes;
     std::vector<int> vc_occupancy;  // [port*num_vcs+vc]
     std::vector<int64_t> link_traffic;
+    std::vector<std::vector<int>> snapshot_data;  // [snapshot][port*num_vcs+vc] dally:867, 5084-5091
 };
 
 struct RunOpts {  // CLI of model-net-synthetic-dragonfly-all synthetic:173-194
@@ -1676,6 +1683,39 @@ public:
         }
     }
 
+    // ============================== router VC-occupancy snapshots ================================
+    // router_send_snapshot_events dally:4363-4417: router 0 writes the header record at init; every router sends itself
+    // one R_SNAPSHOT per configured timestamp (packet_ID = index of the snapshot)
+    void router_send_snapshot_events(uint64_t gid, RouterState& s) {
+        if (s.router_id == 0) {
+            std::string line = "#Time of snapshot,Router ID,";
+            for (int i = 0; i < p.radix; i++)
+                for (int j = 0; j < p.num_vcs; j++) line += fmt("Port %d VC %d,", i, j);
+            line[line.size() - 1] = '\n';
+            lp_io_write("dragonfly-snapshots.csv", line);
+        }
+        for (size_t i = 0; i < p.snapshot_times.size(); i++) {
+            Event& e = ev_new(gid, p.snapshot_times[i], R_SNAPSHOT);
+            e.m.packet_ID = i;
+            ev_send();
+        }
+    }
+    // router_handle_snapshot_event dally:4419-4437 stores the occupancies; the commit handler dally:4687-4709 writes the
+    // record.  A sequential run commits every event right after executing it, so both happen here.
+    void router_handle_snapshot_event(uint64_t gid, const Event& ev) {
+        RouterState& s = rtr[rtr_rel(gid)];
+        size_t k = (size_t)ev.m.packet_ID;
+        if (k >= p.snapshot_times.size()) return;
+        for (int i = 0; i < p.radix; i++)
+            for (int j = 0; j < p.num_vcs; j++) s.snapshot_data[k][i * p.num_vcs + j] = s.vc_occupancy[i * p.num_vcs + j];
+        std::string line = fmt("%.4f, %d, ", p.snapshot_times[k], (int)s.router_id);
+        for (int i = 0; i < p.radix; i++)
+            for (int j = 0; j < p.num_vcs; j++) line += fmt("%d, ", s.snapshot_data[k][i * p.num_vcs + j]);
+        line.resize(line.size() - 2);
+        line += '\n';
+        lp_io_write("dragonfly-snapshots.csv", line);
+    }
+
     // ============================== set-up / run / finalize =====================================
     void init() {
         int n = n_lps();
@@ -1725,6 +1765,10 @@ public:
                 r.vc_occupancy.assign(R * p.num_vcs, 0);
                 r.pending_msgs.assign(R * p.num_vcs, std::deque<Msg>());
                 r.queued_msgs.assign(R * p.num_vcs, std::deque<Msg>());
+                if (!p.snapshot_times.empty()) {  // dally:5084-5091
+                    r.snapshot_data.assign(p.snapshot_times.size(), std::vector<int>((size_t)R * p.num_vcs, 0));
+                    router_send_snapshot_events(g, r);
+                }
             }
         }
     }
@@ -1745,6 +1789,7 @@ public:
         case R_SEND: router_packet_send(gid, ev); break;
         case R_ARRIVE: router_packet_receive(gid, ev); break;
         case R_BUFFER: router_buf_update(gid, ev); break;
+        case R_SNAPSHOT: router_handle_snapshot_event(gid, ev); break;
         default: die("bad event type");
         }
     }

@@ -190,6 +190,9 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
         A.ack_first = (unsigned long long*)(xr + o_af);
         A.ack_last = (unsigned long long*)(xr + o_al);
         A.counters = halloc<unsigned long long>(R, 64);
+        A.snap = halloc<int4>(R, NR * (size_t)P.nsnap_all * radix + 1);
+        A.snap_ts = halloc<double>(R, (size_t)P.nsnap_all + 1);
+        A.snap_id = halloc<unsigned>(R, (size_t)P.nsnap_all + 1);
         {
             std::vector<uint2> geo;
             lane_geometry(P, &geo);
@@ -244,6 +247,10 @@ int dfd_device_upload_topo(DfdDevice* dev, const DfdHostTopo& T, cudaStream_t) {
     for (int i = 0; i < 13; i++) {
         memcpy((void*)dst[i], tabs[i]->data(), tabs[i]->size() * sizeof(int));
         total += tabs[i]->size() * sizeof(int);
+    }
+    for (Rank& R : g_sim->ranks) {
+        memcpy((void*)R.A.snap_ts, T.snap_ts.data(), T.snap_ts.size() * sizeof(double));
+        memcpy((void*)R.A.snap_id, T.snap_id.data(), T.snap_id.size() * sizeof(unsigned));
     }
     dev->topo_bytes = total;
     return 0;
@@ -368,6 +375,7 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t, int) 
     out->node.resize(P.NT);
     out->rh.resize(P.NR);
     out->port.resize((size_t)P.NR * P.radix);
+    out->snap.resize((size_t)P.NR * P.nsnap_all * P.radix);
     out->ack_count.resize(P.NT);
     out->ack_first.resize(P.NT);
     out->ack_last.resize(P.NT);
@@ -376,6 +384,7 @@ int dfd_device_download(DfdDevice* dev, DfdHostResults* out, cudaStream_t, int) 
         memcpy(out->node.data() + R.X.n0, R.A.node, sizeof(NodeState) * R.ntl);
         memcpy(out->rh.data() + R.X.r0, R.A.rh, sizeof(RouterHdr) * R.nrl);
         memcpy(out->port.data() + (size_t)R.X.r0 * P.radix, R.A.port, sizeof(PortState) * (size_t)R.nrl * P.radix);
+        memcpy(out->snap.data() + (size_t)R.X.r0 * P.nsnap_all * P.radix, R.A.snap, sizeof(int4) * (size_t)R.nrl * P.nsnap_all * P.radix);
         memcpy(out->ack_count.data() + R.X.n0, R.A.ack_count, sizeof(unsigned) * R.ntl);
         memcpy(out->ack_first.data() + R.X.n0, R.A.ack_first, 8 * (size_t)R.ntl);
         memcpy(out->ack_last.data() + R.X.n0, R.A.ack_last, 8 * (size_t)R.ntl);

@@ -8,7 +8,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "libdfdally_oracle.so")
 
 EV_NAMES = ["KICKOFF", "REMOTE", "LOCAL", "ACK", "MN_BASE_NEW_MSG", "MN_BASE_SCHED_NEXT", "T_GENERATE", "T_ARRIVE",
-            "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER"]
+            "T_SEND", "T_BUFFER", "R_SEND", "R_ARRIVE", "R_BUFFER", "R_SNAPSHOT"]
 
 
 class Result(ctypes.Structure):
@@ -82,9 +82,12 @@ LPIO_FILES = ["dragonfly-cn-stats", "dragonfly-link-stats", "model-net-category-
               "synthetic-stats", "raw-lp-stats", "summary.txt"]
 
 
+OPTIONAL_FILES = ["dragonfly-snapshots.csv"]  # only with PARAMS router_buffer_snapshots
+
+
 def read_dir(d):
     out = {}
-    for f in LPIO_FILES:
+    for f in LPIO_FILES + OPTIONAL_FILES:
         p = os.path.join(d, f)
         if os.path.exists(p):
             with open(p, "rb") as fh:
@@ -94,7 +97,7 @@ def read_dir(d):
 
 # ---- reference-source oracle: the reference's own sources compiled unchanged against oracle/ref/shim -> oracle/_ref
 REF_BIN = os.path.join(ORACLE_DIR, "_ref", "model-net-synthetic-dragonfly-all")
-REF_FILES = ["dragonfly-cn-stats", "dragonfly-link-stats", "model-net-category-all", "model-net-category-test",
+REF_FILES = ["dragonfly-snapshots.csv", "dragonfly-cn-stats", "dragonfly-link-stats", "model-net-category-all", "model-net-category-test",
              "synthetic-stats"]
 
 

@@ -12,7 +12,7 @@ import pytest
 
 from tests import cpusim_util, oracle_util
 from tests.test_gpu_parity import CASES, VARIANTS, variant_conf
-from tests.test_oracle_cpu import CONF72, CONF1056, CONF8K
+from tests.test_oracle_cpu import CONF72, CONF72SNAP, CONF1056, CONF8K
 
 
 def check(tmp_path, conf, seed, world, warps=None, **opts):
@@ -51,6 +51,12 @@ def test_any_interleaving_gives_the_same_result(tmp_path, seed):
 @pytest.mark.parametrize("world,warps", [(2, None), (3, 2), (8, None)])
 def test_sharded_code_path_emulated_ranks(tmp_path, world, warps):
     check(tmp_path, CONF72, seed=7, world=world, warps=warps, num_messages=12, traffic=3)
+
+
+@pytest.mark.parametrize("world,warps", [(1, 5), (2, None), (4, 3)])
+def test_router_snapshots_sharded_and_pooled(tmp_path, world, warps):
+    """R_SNAPSHOT events (PARAMS router_buffer_snapshots): every rank's records end up in rank 0's dragonfly-snapshots.csv"""
+    check(tmp_path, CONF72SNAP, seed=15 + world, world=world, warps=warps, num_messages=20, traffic=3)
 
 
 def test_several_groups_per_warp(tmp_path):

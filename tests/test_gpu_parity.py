@@ -11,7 +11,7 @@ import pytest
 
 import codes_b200
 from tests import oracle_util
-from tests.test_oracle_cpu import CONF72, CONF1056, CONF8K, GOLDEN, GOLDEN_CASES, parse_cn_stats, parse_link_stats
+from tests.test_oracle_cpu import CONF72, CONF1056, CONF8K, CONF72SNAP, GOLDEN, GOLDEN_CASES, SNAPSHOTS, parse_cn_stats, parse_link_stats, quoted
 
 pytestmark = pytest.mark.gpu
 
@@ -81,9 +81,9 @@ def variant_conf(tmp_path, base, name, **params):
     for k, v in params.items():
         if f"{k}=" in text:
             import re
-            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}="{v}";', text, flags=re.M)
+            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}={quoted(v)};', text, flags=re.M)
         else:
-            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}="{v}";')
+            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}={quoted(v)};')
     p = tmp_path / (name + ".conf")
     p.write_text(text)
     return str(p)
@@ -106,6 +106,15 @@ VARIANTS = [
     ("72-big-payload", CONF72, dict(), dict(num_messages=5, payload_sz=20000)),                        # 5 packets per message
     ("1056-nonminimal", CONF1056, dict(routing="nonminimal"), dict(num_messages=4)),
     ("1056-par", CONF1056, dict(routing="prog-adaptive", adaptive_threshold="16384"), dict(num_messages=6, traffic=3)),
+    # router VC-occupancy snapshots (PARAMS router_buffer_snapshots -> dragonfly-snapshots.csv; dally:4363-4437, 4687-4709):
+    # unsorted times, one past the last packet, one past --end, equal times, long after the network has drained
+    ("72-snapshots", CONF72, dict(router_buffer_snapshots=SNAPSHOTS), dict(num_messages=20)),
+    ("72-snapshots-par-nearest-group", CONF72, dict(router_buffer_snapshots=SNAPSHOTS, routing="prog-adaptive", adaptive_threshold="0"),
+     dict(num_messages=20, traffic=3)),
+    ("72-snapshots-end", CONF72, dict(router_buffer_snapshots=SNAPSHOTS), dict(num_messages=20, end_time=10000.0)),
+    ("72-snapshots-far", CONF72, dict(router_buffer_snapshots='( "250000" )'), dict(num_messages=3)),
+    ("72-snapshots-equal-times", CONF72, dict(router_buffer_snapshots='( "5000","5000" )'), dict(num_messages=10, traffic=3)),
+    ("1056-snapshots", CONF1056, dict(router_buffer_snapshots='( "4000","9000" )'), dict(num_messages=5, traffic=3)),
 ]
 
 
@@ -189,6 +198,7 @@ def test_large_partition_kernel_matches_oracle(tmp_path, monkeypatch, name, conf
 
 
 POOL_CASES = NARROW_CASES + [
+    ("72-snapshots-nearest-group", CONF72SNAP, dict(num_messages=20, traffic=3)),  # R_SNAPSHOT events in the pick (horizon in its own pass)
     ("72-multichunk", CONF72, dict(num_messages=5, payload_sz=10000)),
     ("8320-par-uniform", CONF8K, dict(num_messages=3)),
 ]
@@ -331,7 +341,8 @@ def test_engine_matches_oracle_parallel_local_links(tmp_path, name, radix, conns
 
 @pytest.mark.parametrize("world,conf,opts", [(2, CONF72, dict(num_messages=20)), (3, CONF72, dict(num_messages=10, traffic=3)),
                                              (4, CONF1056, dict(num_messages=10)), (2, CONF1056, dict(num_messages=5, payload_sz=10000)),
-                                             (8, CONF8K, dict(num_messages=3, traffic=3))])
+                                             (8, CONF8K, dict(num_messages=3, traffic=3)),
+                                             (3, CONF72SNAP, dict(num_messages=20, traffic=3))])  # snapshot records gathered from every rank
 def test_group_sharded_ranks_on_one_gpu_match_oracle(tmp_path, world, conf, opts):
     """The group-sharded engine with all ranks on this one GPU: cross-rank lanes, channel words, ACK statistics,
     termination detection over several control blocks and rank 0's gather of the partitions must give the sequential

@@ -12,6 +12,7 @@ ROOT = oracle_util.ROOT
 CONF72 = os.path.join(ROOT, "configs", "dfdally-72.conf")
 CONF1056 = os.path.join(ROOT, "configs", "dfdally-1056.conf")
 CONF8K = os.path.join(ROOT, "configs", "dfdally-8320-par.conf")
+CONF72SNAP = os.path.join(ROOT, "configs", "dfdally-72-snapshots.conf")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 M = [2147483647, 2147483543, 2147483423, 2147483323]
@@ -167,6 +168,8 @@ GOLDEN_CASES = {
     "72_nearest_group_m10": dict(conf=CONF72, num_messages=10, traffic=3),
     "1056_uniform_m5": dict(conf=CONF1056, num_messages=5, traffic=1),
     "8320_par_uniform_m2": dict(conf=CONF8K, num_messages=2, traffic=1),
+    # router VC-occupancy snapshots (PARAMS router_buffer_snapshots -> dragonfly-snapshots.csv), congested traffic
+    "72_snapshots_nearest_group_m20": dict(conf=CONF72SNAP, num_messages=20, traffic=3),
 }
 
 
@@ -244,6 +247,14 @@ def test_restatement_matches_reference_sources(tmp_path, ref_oracle, name, conf,
     assert oracle_util.stdout_stats_block(out) == oracle_util.stdout_stats_block(o["summary.txt"].decode())
 
 
+def quoted(v):
+    """a list value ( "a","b" ) is written as it is, a scalar in quotes"""
+    return v if v.startswith("(") else f'"{v}"'
+
+
+SNAPSHOTS = '( "3000","12000.5","8000","16000" )'
+
+
 def ref_variant(tmp_path, base, **params):
     import re
     with open(base) as f:
@@ -252,9 +263,9 @@ def ref_variant(tmp_path, base, **params):
     text = text.replace(f'"{stem}-intra"', f'"{d}/{stem}-intra"').replace(f'"{stem}-inter"', f'"{d}/{stem}-inter"')
     for k, v in params.items():
         if re.search(r'^\s*' + re.escape(k) + r'\s*=', text, flags=re.M):
-            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}="{v}";', text, flags=re.M)
+            text = re.sub(r'^\s*' + re.escape(k) + r'\s*=.*$', f'   {k}={quoted(v)};', text, flags=re.M)
         else:
-            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}="{v}";')
+            text = text.replace("PARAMS\n{", "PARAMS\n{\n   " + f'{k}={quoted(v)};')
     p = tmp_path / "variant.conf"
     p.write_text(text)
     return str(p)
@@ -274,6 +285,14 @@ REF_VARIANTS = [
     ("72-self-copy-bypass", CONF72, dict(codes_noop_bypass="1"), dict(num_messages=12, traffic=2)),
     ("72-self-copy-eager-limit", CONF72, dict(node_eager_limit="100"), dict(num_messages=12, traffic=2, payload_sz=4096, arrival_time=300.0)),
     ("1056-par", CONF1056, dict(routing="prog-adaptive", adaptive_threshold="16384"), dict(num_messages=4, traffic=3)),
+    # router VC-occupancy snapshots (dally:4363-4437, 4687-4709): unsorted times, one past the last packet, one past --end
+    ("72-snapshots", CONF72, dict(router_buffer_snapshots=SNAPSHOTS), dict(num_messages=20)),
+    ("72-snapshots-par-nearest-group", CONF72, dict(router_buffer_snapshots=SNAPSHOTS, routing="prog-adaptive", adaptive_threshold="0"),
+     dict(num_messages=20, traffic=3)),
+    ("72-snapshots-end", CONF72, dict(router_buffer_snapshots=SNAPSHOTS), dict(num_messages=20, end_time=10000.0)),
+    ("72-snapshots-far", CONF72, dict(router_buffer_snapshots='( "250000" )'), dict(num_messages=3)),  # long after the network has drained
+    ("72-snapshots-equal-times", CONF72, dict(router_buffer_snapshots='( "5000","5000" )'), dict(num_messages=10, traffic=3)),
+    ("1056-snapshots", CONF1056, dict(router_buffer_snapshots='( "4000","9000" )'), dict(num_messages=5, traffic=3)),
 ]
 
 
