@@ -73,6 +73,9 @@ def make_case(rng):
         params["node_eager_limit"] = rng.choice(["0", "100", "5000", "100000"])
         if rng.random() < 0.5:
             params["codes_noop_bypass"] = rng.choice(["0", "1"])
+    if rng.random() < 0.2:  # router VC-occupancy snapshots (dragonfly-snapshots.csv): unsorted, possibly equal or past the end
+        times = [rng.choice(["500", "2500.5", "6000", "6000", "15000", "60000"]) for _ in range(rng.randint(1, 3))]
+        params["router_buffer_snapshots"] = "( " + ",".join(f'"{t}"' for t in times) + " )"
     return radix, conns, routing, params, opts
 
 

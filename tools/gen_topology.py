@@ -113,7 +113,8 @@ def write_config(out_dir, name, radix, conns, routing="minimal", packet_size=409
             overrides[arg] = ex.pop(key)
     local_vc, global_vc, cn_vc = (overrides.get("local_vc", local_vc), overrides.get("global_vc", global_vc), overrides.get("cn_vc", cn_vc))
     bws = {k: ex.pop(k) for k in ("local_bandwidth", "global_bandwidth", "cn_bandwidth") if k in ex}
-    extra_lines = "".join(f'   {k}="{v}";\n' for k, v in ex.items())
+    # a list value, e.g. router_buffer_snapshots=( "3000","8000" ), is written as it is
+    extra_lines = "".join(f'   {k}={v};\n' if v.startswith("(") else f'   {k}="{v}";\n' for k, v in ex.items())
     with open(conf, "w") as f:
         # link files are written relative to the .conf (resolved against its directory)
         text = CONF_TEMPLATE.format(reps=a * g, p=p, a=a, g=g, h=h, packet_size=packet_size,
