@@ -110,19 +110,21 @@ def check_against_golden(out_dir, gold_name):
     return gold
 
 
-CASES = [("72_uniform_m1", ["--traffic=1", "--num_messages=1"]), ("72_uniform_m20", ["--traffic=1", "--num_messages=20"]),
-         ("72_nearest_group_m10", ["--traffic=3", "--num_messages=10"])]
+CONF72 = os.path.join(ROOT, "configs", "dfdally-72.conf")
+CASES = [("72_uniform_m1", CONF72, ["--traffic=1", "--num_messages=1"]), ("72_uniform_m20", CONF72, ["--traffic=1", "--num_messages=20"]),
+         ("72_nearest_group_m10", CONF72, ["--traffic=3", "--num_messages=10"]),
+         # PARAMS router_buffer_snapshots: dragonfly-snapshots.csv through the drivers' own lp_io_flush
+         ("72_snapshots_nearest_group_m20", os.path.join(ROOT, "configs", "dfdally-72-snapshots.conf"), ["--traffic=3", "--num_messages=20"])]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gold_name,args", CASES, ids=[c[0] for c in CASES])
-def test_reference_main_on_the_engine_matches_golden(tmp_path, gold_name, args):
+@pytest.mark.parametrize("gold_name,conf,args", CASES, ids=[c[0] for c in CASES])
+def test_reference_main_on_the_engine_matches_golden(tmp_path, gold_name, conf, args):
     """The reference's own main() (unmodified source, compiled in the authoring container) with tw_run() on the B200."""
     if not os.path.exists(REFMAIN):
         pytest.skip("codes_b200/_refmain is built where the reference tree exists and travels with the snapshot")
     out = str(tmp_path / "lpio")
-    r = subprocess.run([REFMAIN, "--sync=1", *args, f"--lp-io-dir={out}", "--", os.path.join(ROOT, "configs", "dfdally-72.conf")],
-                       capture_output=True, text=True)
+    r = subprocess.run([REFMAIN, "--sync=1", *args, f"--lp-io-dir={out}", "--", conf], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     gold = check_against_golden(out, gold_name)
     m = re.search(r"Net Events Processed\s+(\d+)", r.stdout)
@@ -131,11 +133,10 @@ def test_reference_main_on_the_engine_matches_golden(tmp_path, gold_name, args):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("gold_name,args", CASES, ids=[c[0] for c in CASES])
-def test_c_twin_driver_matches_golden(tmp_path, gold_name, args):
+@pytest.mark.parametrize("gold_name,conf,args", CASES, ids=[c[0] for c in CASES])
+def test_c_twin_driver_matches_golden(tmp_path, gold_name, conf, args):
     """codes_b200/model-net-synthetic-dragonfly-all (csrc/synthetic_main.c): same command line through the dfd_* C-ABI."""
     out = str(tmp_path / "lpio")
-    r = subprocess.run([TWIN, "--sync=1", *args, f"--lp-io-dir={out}", "--", os.path.join(ROOT, "configs", "dfdally-72.conf")],
-                       capture_output=True, text=True)
+    r = subprocess.run([TWIN, "--sync=1", *args, f"--lp-io-dir={out}", "--", conf], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     check_against_golden(out, gold_name)
