@@ -22,6 +22,7 @@ CASES = [
     ("configs/dfdally-1056.conf", dict(num_messages=10)),
     ("configs/dfdally-8320-par.conf", dict(num_messages=3, traffic=3)),
     ("configs/dfdally-1056.conf", dict(num_messages=5, payload_sz=10000)),   # multi-packet messages across GPUs
+    ("configs/dfdally-72-snapshots.conf", dict(num_messages=20, traffic=3)),  # R_SNAPSHOT records gathered from every GPU
 ]
 
 
