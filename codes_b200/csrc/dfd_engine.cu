@@ -489,7 +489,10 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     // Event budget of one activation.  With a warp per group the run is bound by the chain of dependent activations:
     // publishing early lets the neighbours start.  With several groups per warp it is bound by throughput: the fixed
     // cost of an activation (poll, bounds, publish) is spread over more events.
-    if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->warps ? 16 : 4;
+    // With a warp per group the best budget grows with the radix -- the fixed cost of an activation does -- measured on B200
+    // (tools/gpu_batch24.sh): radix 15: 2 (13.9 M events/s against 12.7 M with 4), radix 31: 4-6, radix 63: 10-12 (178 M against
+    // 154 M with 4 on 1,056 routers, 196 M against 170 M on 2,080).
+    if (!getenv("DFD_ACT_BUDGET")) dev->P.act_budget = groups > (size_t)dev->warps ? 16 : std::max(2, std::min(16, P.radix / 6));
     // Idle warps of a throughput-bound run compete with the busy ones for instruction fetch: let them pause.  With a
     // warp per group the poll latency is on the critical path: no pause.
     dev->P.idle_sleep_ns = groups > (size_t)dev->warps ? 8000 : 0;
