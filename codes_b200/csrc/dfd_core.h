@@ -60,6 +60,13 @@ DFD_FN void st_strong64(unsigned long long* p, unsigned long long v, bool sys) {
     else
         asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// one 16-byte access, single-copy atomic (PTX .b128 scalar type): an entry of a publisher queue
+DFD_FN void st_relaxed_b128(void* p, unsigned long long lo, unsigned long long hi) {
+    asm volatile("{ .reg .b128 t; mov.b128 t, {%1, %2}; st.relaxed.gpu.global.b128 [%0], t; }" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+DFD_FN void ld_relaxed_b128(const void* p, unsigned long long& lo, unsigned long long& hi) {
+    asm volatile("{ .reg .b128 t; ld.relaxed.gpu.global.b128 t, [%2]; mov.b128 {%0, %1}, t; }" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
 // release fence without the L1 invalidation an acq_rel fence carries (SASS: MEMBAR.ALL.{GPU,SYS}, no CCTL.IVALL):
 // LP-private state stays L1-resident, everything another LP writes is read with ld.cg / ld.relaxed (L2)
 DFD_FN void fence_release(bool sys) {
@@ -2009,6 +2016,28 @@ DFD_FN void ctx_bind_group(Ctx& c, unsigned rl) {
     c.iblk = A.iblk + (size_t)rl * 2 * P.p;
 }
 
+// Channel word to a neighbour.  Sharded runs with publisher queues (DfdParams::npubq, see PubCtl): a word whose target lives on
+// another rank is handed to this group's publisher queue instead of being stored behind a system-scope fence of this warp.
+DFD_FN void publish_word(const Ctx& c, unsigned long long* target, unsigned long long w, bool sys) {
+#ifdef __CUDACC__
+    const DfdParams& P = *c.P;
+    if (P.npubq && (unsigned long long)((const char*)target - c.X->local_base) >= c.X->local_bytes) {
+        const DfdArrays& A = *c.A;
+        const unsigned qi = c.rl % (unsigned)P.npubq;
+        PubCtl* ctl = &A.pubctl[qi];
+        const unsigned long long t = atomicAdd(&ctl->reserve, 1ULL);
+        while (t - ld_strong64(&ctl->head) >= (unsigned long long)DFD_PUBQ_CAP) {  // ring full: wait for the publisher
+            if (ld_strong64(&A.ctrl->error) | ld_strong64(&A.ctrl->done)) return;
+            __nanosleep(200);
+        }
+        const unsigned long long tag = (t / DFD_PUBQ_CAP) % 3ULL + 1ULL;
+        st_relaxed_b128(&A.pubq[(size_t)qi * DFD_PUBQ_CAP + (t & (DFD_PUBQ_CAP - 1))], (unsigned long long)target | tag, w);
+        return;
+    }
+#endif
+    st_strong64(target, w, sys);
+}
+
 struct ActResult {
     unsigned nexec;  // events executed (warp total)
     bool polled_change;
@@ -2223,7 +2252,7 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
     const bool sys = X.world > 1;
     if (total | created) {
         if (IS_LANE0() && created) red_add_i64((long long*)&A.ctrl->created, (long long)created, sys);
-        fence_release(sys);
+        fence_release(sys && P.npubq == 0);  // with publisher queues the system-scope fence is the publisher's
         if (IS_LANE0() && total) red_add_i64((long long*)&A.ctrl->consumed, (long long)total, sys);
     }
     {
@@ -2279,7 +2308,7 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
                 unsigned long long old = pubc[q];
                 if (w != old && (((w ^ old) & DFD_STAMP_MASK) != 0 || old == ~0ULL || !(bound < cw_bound(old) + (loc ? P.hyst_local : P.hyst_global)))) {
                     pubc[q] = w;
-                    st_strong64(tc, w, sys);
+                    publish_word(c, tc, w, sys);
                 }
             }
             // credit bound of my in-lane q -> channel word of the port that feeds it
@@ -2291,7 +2320,7 @@ template <bool SPLIT = false> DFD_FN ActResult group_activate(Ctx& c, unsigned r
                 unsigned long long w = cw_pack(cd + mind(a_in, late_credit_bound(c, q)), L.sent_k);
                 if (w != pubk[q]) {
                     pubk[q] = w;
-                    st_strong64(tk, w, sys);
+                    publish_word(c, tk, w, sys);
                 }
             }
         }

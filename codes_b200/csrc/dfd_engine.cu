@@ -59,6 +59,57 @@ __device__ bool monitor_check(const DfdArrays& A, const DfdPeers& X, unsigned lo
     return false;
 }
 
+// Publisher of queue qi (sharded runs; PubCtl in dfd_types.h): takes the entries that are ready, executes ONE system-scope
+// fence for the batch and stores the channel words into the other ranks' memory.  Within a batch the last entry for a
+// target wins (a newer word supersedes an older one: counts and bounds only grow).
+__device__ void publisher_loop(const DfdParams& P, const DfdArrays& A, unsigned qi) {
+    // chunks of 32 entries per batch.  1 is what was validated on 2, 4 and 8 GPUs; 4 (up to 128 words per fence) passes the
+    // ranks-on-one-GPU tests and was not faster there
+    constexpr int CH = 1;
+    const int lane = DFD_LANE();
+    const ulonglong2* q = A.pubq + (size_t)qi * DFD_PUBQ_CAP;
+    PubCtl* ctl = &A.pubctl[qi];
+    unsigned long long head = 0;
+    for (;;) {
+        unsigned long long a[CH], b[CH];
+        int n = 0;  // entries ready in ticket order
+        bool open = true;
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            const unsigned long long t = head + (unsigned)(32 * j + lane);
+            ld_relaxed_b128(&q[t & (DFD_PUBQ_CAP - 1)], a[j], b[j]);
+            const bool ok = (a[j] & 7ULL) == (t / DFD_PUBQ_CAP) % 3ULL + 1ULL;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (open) {
+                if (m == 0xFFFFFFFFu)
+                    n += 32;
+                else {
+                    n += __ffs((int)~m) - 1;
+                    open = false;
+                }
+            }
+        }
+        if (n == 0) {
+            if (ld_strong64(&A.ctrl->error) | ld_strong64(&A.ctrl->done)) break;
+            __nanosleep(100);
+            continue;
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            // inside a chunk the last entry for a target wins (one instruction: no order among its lanes); a later chunk
+            // overwrites an earlier one: __syncwarp orders the stores of two chunks, and both are system-scope stores to one location
+            const bool mine = 32 * j + lane < n;
+            const unsigned long long tgt = a[j] & ~7ULL;
+            const unsigned same = __match_any_sync(0xFFFFFFFFu, mine ? tgt : (unsigned long long)lane);  // real targets are pointers: never < 32
+            if (mine && (31 - __clz((int)same)) == lane) st_strong64((unsigned long long*)tgt, b[j], true);
+            __syncwarp();
+        }
+        head += (unsigned)n;
+        if (lane == 0) st_strong64(&ctl->head, head, false);
+    }
+}
+
 // What a warp accumulates over its life and folds into the run counters when it leaves the event loop.
 struct WarpTally {
     unsigned long long n_act = 0, n_prod = 0, n_exec = 0, passes = 0;
@@ -100,7 +151,11 @@ __global__ void __launch_bounds__(32, MIN_BLOCKS) dfd_run_kernel(DfdParams P, Df
     Ctx c;
     ctx_init(c, &P, &A, &X, s_ev);
     const unsigned ngroups = (unsigned)(X.r1 - X.r0);
-    const unsigned w = blockIdx.x, nw = gridDim.x;
+    const unsigned w = blockIdx.x, nw = gridDim.x - (unsigned)P.npub_blocks;
+    if (w >= nw) {  // the last blocks of the grid are the publishers of a sharded run
+        publisher_loop(P, A, w - nw);
+        return;
+    }
     WarpTally t;
     unsigned long long idle_passes = 0;
     unsigned long long last_consumed = ~0ULL, last_change_ns = globaltimer_ns();
@@ -156,7 +211,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) dfd_run_kernel_pool(DfdParams P
     const int lane = DFD_LANE();
     const unsigned wib = threadIdx.x >> 5;
     const unsigned ngroups = (unsigned)(X.r1 - X.r0);
-    const unsigned b = blockIdx.x, nb = gridDim.x;
+    const unsigned b = blockIdx.x, nb = gridDim.x - (unsigned)P.npub_blocks;
+    if (b >= nb) {  // publisher block of a sharded run: one queue per warp
+        const unsigned qi = (b - nb) * WARPS + wib;
+        if (qi < (unsigned)P.npubq) publisher_loop(P, A, qi);
+        return;
+    }
     const unsigned g0 = (unsigned)(((unsigned long long)ngroups * b) / nb), g1 = (unsigned)(((unsigned long long)ngroups * (b + 1)) / nb);
     const unsigned ng = g1 - g0;
     for (unsigned i = threadIdx.x; i < ng; i += blockDim.x) s_lock[i] = 0;
@@ -226,6 +286,8 @@ __global__ void dfd_init_kernel(DfdParams P, DfdArrays A, DfdPeers X, DfdSeedCon
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ntl = (size_t)(X.n1 - X.n0), nrl = (size_t)(X.r1 - X.r0);
     if (gtid == 0) init_ctrl(P, A, X);
+    for (size_t i = gtid; i < (size_t)P.npubq * DFD_PUBQ_CAP; i += nthreads) A.pubq[i] = make_ulonglong2(0ULL, 0ULL);
+    for (size_t i = gtid; i < (size_t)P.npubq; i += nthreads) A.pubctl[i].reserve = A.pubctl[i].head = 0ULL;
     for (size_t n = gtid; n < ntl; n += nthreads) init_node(P, A, X, K, (unsigned)n);
     for (size_t r = gtid; r < nrl; r += nthreads) init_router(P, A, X, K, (unsigned)r);
     for (size_t i = gtid; i < nrl * P.radix; i += nthreads) init_lane(P, A, X, i);
@@ -421,6 +483,7 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     for (int k = 0; k < DFD_MAX_RANKS; k++) dev->X.base[k] = nullptr;
     dev->X.base[rank] = xr;
     dev->X.local_base = xr;
+    dev->X.local_bytes = off;
     {
         std::vector<uint2> geo;
         lane_geometry(P, &geo);
@@ -461,14 +524,30 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
     dev->blocks_per_sm = per_sm;
     size_t slots_total = (size_t)per_sm * dev->num_sms;
     if (ensemble > 1) slots_total = std::max<size_t>(1, slots_total / ensemble);  // the GPU is shared by `ensemble` engines
-    dev->grid = (int)std::max<size_t>(1, std::min(groups, slots_total));
+    // Sharded runs: the last blocks of the grid are publishers (PubCtl in dfd_types.h); DFD_NPUB=0 goes back to one system-scope
+    // fence per activation
+    // One warp per group: an activation that ends in fence.release.sys stalls its group for 5 us at N=8 (a run with gpu-scope
+    // fences, timing only, is 24 % faster), so the words for other ranks can go through publisher blocks: as many as fit beside
+    // the groups, 4..32 (a publisher moves at most 32 words per fence).  The word still reaches the other rank only after a
+    // system-scope fence -- the publisher's -- so what is gained is the stall, not the latency: measured on the bench network,
+    // 8 GPUs (1,028 groups per GPU) 980 M events/s with publishers against 940 M without; 4 GPUs (2,056 groups per GPU, twice the
+    // words per GPU) 576 M against 619 M; 2 GPUs (pooled kernel, whose other warps hide the fence) 370 M against 425 M.  Hence:
+    // publishers only for partitions of at most 8 groups per SM (the 226-register kernel), and for ranks that share a GPU (tests).
+    int npub_blocks = 0;
+    if (world > 1 && ensemble > 1) npub_blocks = 1;
+    if (world > 1 && ensemble <= 1 && wide) npub_blocks = (int)std::max<long long>(4, std::min<long long>(32, (long long)slots_total - (long long)groups));
+    if (const char* ev = getenv("DFD_NPUB")) npub_blocks = world > 1 ? std::max(0, std::min(16, atoi(ev))) : 0;
+    if (slots_total < (size_t)npub_blocks + 1) npub_blocks = 0;
+    dev->grid = (int)std::max<size_t>(1, std::min(groups, slots_total - npub_blocks));
     if (const char* ev = getenv("DFD_GRID")) dev->grid = std::max(1, std::min(dev->grid, atoi(ev)));
+    int npubq = npub_blocks;  // one warp per block: one queue per publisher block
     // More groups than resident warps: one 16-warp block per SM whose warps share the block's groups (dfd_run_kernel_pool)
     bool pool = groups > (size_t)dev->grid && ensemble <= 1 && !getenv("DFD_GRID") && !getenv("DFD_MINBLOCKS");
     if (const char* ev = getenv("DFD_POOL")) pool = atoi(ev) != 0 && ensemble <= 1;
     if (pool) {
         constexpr int W = DFD_POOL_WARPS;
-        const int nb = (int)std::min<size_t>((size_t)dev->num_sms, (groups + W - 1) / W);
+        const int pool_pub = npub_blocks && getenv("DFD_POOL_PUB") ? 1 : 0;  // (experiment) one publisher block of W warps: W queues
+        const int nb = (int)std::min<size_t>((size_t)dev->num_sms - pool_pub, (groups + W - 1) / W);
         const size_t per_block = (groups + nb - 1) / nb;
         const size_t smem = per_block * sizeof(unsigned);
         const void* k = (const void*)dfd_run_kernel_pool<W>;
@@ -483,9 +562,16 @@ int dfd_device_create(DfdDevice* dev, const DfdParams& P, const DfdHostTopo& T, 
             dev->grid = nb;
             dev->smem = smem;
             dev->blocks_per_sm = 1;
+            npub_blocks = pool_pub;
+            npubq = pool_pub * W;
         }
     }
-    dev->warps = dev->grid * (dev->block / 32);
+    dev->warps = dev->grid * (dev->block / 32);  // worker warps
+    dev->grid += npub_blocks;
+    dev->P.npub_blocks = npub_blocks;
+    dev->P.npubq = npubq;
+    if (dalloc(dev, &A.pubq, (size_t)npubq * DFD_PUBQ_CAP)) return 1;
+    if (dalloc(dev, &A.pubctl, (size_t)npubq)) return 1;
     // Event budget of one activation.  With a warp per group the run is bound by the chain of dependent activations:
     // publishing early lets the neighbours start.  With several groups per warp it is bound by throughput: the fixed
     // cost of an activation (poll, bounds, publish) is spread over more events.

@@ -1186,10 +1186,13 @@ int dfd_engine_upload(dfd_engine* e, void* stream) {
     }
     if (reuse) {
         const int budget = e->dev.P.act_budget, idle_sleep = e->dev.P.idle_sleep_ns, prefetch = e->dev.P.prefetch;  // chosen by dfd_device_create from the grid it sized
+        const int npubq = e->dev.P.npubq, npub_blocks = e->dev.P.npub_blocks;
         e->dev.P = P;
         if (!getenv("DFD_ACT_BUDGET")) e->dev.P.act_budget = budget;
         e->dev.P.idle_sleep_ns = idle_sleep;
         e->dev.P.prefetch = prefetch;
+        e->dev.P.npubq = npubq;
+        e->dev.P.npub_blocks = npub_blocks;
     } else {
         if (e->device_ready) {
             dfd_device_destroy(&e->dev);

@@ -295,6 +295,7 @@ struct DfdParams {
     int ext;                           // intra_radix + global_radix: lanes / ports [0, ext) connect routers, [ext, radix) terminals
     int idle_sleep_ns;                 // pause of a warp after a pass over its groups that executed nothing (0: poll again at once)
     int act_budget;                    // router events after which an activation publishes its bounds even if more would be safe
+    int npubq, npub_blocks;            // sharded runs: publisher queues / publisher blocks at the end of the grid (0: every activation ends in its own system-scope fence)
     int nsnap, nsnap_all;              // R_SNAPSHOT events per router: those before ts_end (the ones that exist) / configured
     int prefetch;                      // an activation that gets past the poll prefetches the router's port state into L1 (partitions larger than L2)
 };
@@ -315,6 +316,21 @@ struct DfdCtrl {
     unsigned long long error_info;
     unsigned long long done;      // set by this rank's monitor warp
     unsigned long long pad[27];
+};
+
+// Publisher queues (sharded runs).  fence.release.sys costs 2,800 cycles on B200 with nothing outstanding and 10,000 when a
+// thousand warps issue it concurrently (tools/ubench/fence_sys.cu) -- a fifth of an 8-GPU run when every activation ends in one.
+// So an activation ends in a gpu-scope release fence (700 cycles) and hands the channel words that go to ANOTHER rank to a
+// publisher warp: {target | tag, word} entries in a multi-producer ring, one 16-byte relaxed store each.  The publisher
+// takes a batch of entries, executes ONE fence.acq_rel.sys -- fences are cumulative: the records the producers wrote before their
+// own release fences are ordered before it -- and stores the words with st.relaxed.sys.  Words of one source group always
+// travel through the same queue, so they reach their target in order.
+#define DFD_PUBQ_CAP 8192  // entries per queue (power of two)
+struct PubCtl {
+    unsigned long long reserve;  // next ticket (producers, atomicAdd)
+    unsigned long long pad0[15];
+    unsigned long long head;     // entries the publisher is done with (back-pressure)
+    unsigned long long pad1[15];
 };
 
 // device arrays.  Everything indexed by router / node uses the LOCAL index inside this rank's partition.
@@ -360,6 +376,8 @@ struct DfdArrays {
     ChunkRec* ring_c;            // [NRmax][cslots]
     Key* ring_k;                 // [NRmax][kslots]
     DfdCtrl* ctrl;
+    ulonglong2* pubq;       // [npubq][DFD_PUBQ_CAP] {target pointer | tag in the low 3 bits, channel word}
+    PubCtl* pubctl;         // [npubq]
     int4* snap;             // [NRmax][nsnap_all][radix] vc_occupancy[port][0..3] captured by R_SNAPSHOT number i (statistics: exchange region)
     const double* snap_ts;  // [nsnap]  snapshot times before ts_end, sorted by (time, configured index)
     const unsigned* snap_id; // [nsnap] configured index of each (= packet_ID = sequence number of the event, dally:4407-4414)
@@ -394,6 +412,7 @@ struct DfdPeers {
     int n0, n1, r0, r1;                 // owned node / router ranges (global ids)
     char* base[DFD_MAX_RANKS];          // exchange-region base of every rank as mapped into this process
     char* local_base;                   // == base[rank]
+    unsigned long long local_bytes;     // size of this rank's exchange region: a channel-word target outside it lives on another rank
 };
 
 enum { DFD_ERR_NONE = 0, DFD_ERR_NEV_OVERFLOW = 1, DFD_ERR_SQ_OVERFLOW, DFD_ERR_TQ_OVERFLOW, DFD_ERR_POOL_OVERFLOW,

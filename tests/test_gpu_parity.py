@@ -357,6 +357,20 @@ def test_group_sharded_ranks_on_one_gpu_match_oracle(tmp_path, world, conf, opts
         assert g[name] == r[name], f"{name} differs"
 
 
+def test_group_sharded_ranks_without_publisher_queues(tmp_path, monkeypatch):
+    """Sharded runs hand the channel words for other ranks to publisher blocks (one system-scope fence per batch);
+    DFD_NPUB=0 is the direct path: every activation ends in its own system-scope fence (what the pooled kernel always does)."""
+    monkeypatch.setenv("DFD_NPUB", "0")
+    gdir, odir = str(tmp_path / "gpu"), str(tmp_path / "oracle")
+    opts = dict(num_messages=10, traffic=3)
+    s = codes_b200.run_sharded_local(CONF1056, 4, lp_io_dir=gdir, **opts)
+    o = oracle_util.run(CONF1056, lp_io_dir=odir, **opts)
+    assert s.events == o.events
+    g, r = oracle_util.read_dir(gdir), oracle_util.read_dir(odir)
+    for name in r:
+        assert g[name] == r[name], f"{name} differs"
+
+
 def test_multi_process_sharding_when_two_gpus_are_present():
     """torchrun with one process per GPU (CUDA-IPC exchange regions over NVLink): tests/mgpu_check.py."""
     import torch
