@@ -1,5 +1,5 @@
 #!/bin/bash
-# poll backoff in the pooled kernel: bench network (131,584 terminals, PAR, uniform), 10 and 50 messages per terminal
+# poll backoff in the pooled kernel (needs experiments/poll_backoff.patch applied): bench network, 10 and 50 messages per terminal
 cd "$(dirname "$0")/.."
 cat > /tmp/b18.py <<'PY'
 import os, sys, subprocess, tempfile
