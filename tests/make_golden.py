@@ -73,7 +73,7 @@ def large(which):
         case = dict(num_messages=msgs, traffic=traffic)
         res = oracle_util.run(conf, lp_io_dir=os.path.join(tmp, "out"), **case)
         out = oracle_util.read_dir(os.path.join(tmp, "out"))
-        # oracle/_ref does not finish these sizes in 15 minutes (the reference's set-up is super-linear in the LP count);
+        # oracle/_ref needs 14 minutes and 20-28 GB per 131,584-terminal case (tools/ref_check_large.py runs it and records the check);
         # the restatement is pinned to it on the smaller cases of tests/test_oracle_cpu.py
         meta = dict(conf=f"tools/gen_topology.py {radix} {conns} <dir> --name big --routing {routing}", options=case, events=res.events,
                     generated_by="oracle/dfdally_oracle.cpp (restatement oracle)",
