@@ -293,6 +293,7 @@ REF_VARIANTS = [
     ("72-snapshots-far", CONF72, dict(router_buffer_snapshots='( "250000" )'), dict(num_messages=3)),  # long after the network has drained
     ("72-snapshots-equal-times", CONF72, dict(router_buffer_snapshots='( "5000","5000" )'), dict(num_messages=10, traffic=3)),
     ("1056-snapshots", CONF1056, dict(router_buffer_snapshots='( "4000","9000" )'), dict(num_messages=5, traffic=3)),
+    ("8320-par-snapshots", CONF8K, dict(router_buffer_snapshots='( "4000","2000","9000.25" )'), dict(num_messages=2, traffic=3)),
 ]
 
 
