@@ -221,6 +221,8 @@ LARGE_GOLDEN = [
     ("131584_par_nearest_group_m3", 64, 2, 131584, 3, "prog-adaptive", 3),  # configs[3]: PAR, worst-case group permutation
     ("1050624_uniform_m1", 128, 4, 1050624, 1, "minimal", 1),  # BASELINE configs[4] scale: a=64, p=32, h=32, g=513, 32,832 routers
 ]
+if os.environ.get("DFD_LONG_TESTS"):  # the bench network in a long run (saturated: 154.6 M events, 1.2 s of kernel, 6 GB of host text to hash)
+    LARGE_GOLDEN.append(("131584_par_uniform_m50", 64, 2, 131584, 50, "prog-adaptive", 1))
 
 
 @pytest.mark.parametrize("gold_name,radix,conns,n,msgs,routing,traffic", LARGE_GOLDEN, ids=[g[0] for g in LARGE_GOLDEN])
