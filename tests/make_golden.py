@@ -56,6 +56,7 @@ LARGE = {
     "131584_par_nearest_group_m3": (64, 2, 131584, 3, "prog-adaptive", 3),  # BASELINE configs[3]: PAR, worst-case group permutation
     "131584_par_uniform_m10": (64, 2, 131584, 10, "prog-adaptive", 1),  # bench.py's workload (parity_digest_ok)
     "131584_par_uniform_m50": (64, 2, 131584, 50, "prog-adaptive", 1),  # the same in a long run: saturated network (154.6 M events, ~8 min)
+    "131584_par_nearest_group_m50": (64, 2, 131584, 50, "prog-adaptive", 3),  # configs[3] in a long run (173.2 M events)
     "1050624_uniform_m1": (128, 4, 1050624, 1, "minimal", 1),  # a=64, p=32, h=32, g=513   (~2 min, 1 GB of lp-io text)
 }
 

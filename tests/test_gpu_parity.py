@@ -223,6 +223,7 @@ LARGE_GOLDEN = [
 ]
 if os.environ.get("DFD_LONG_TESTS"):  # the bench network in a long run (saturated: 154.6 M events, 1.2 s of kernel, 6 GB of host text to hash)
     LARGE_GOLDEN.append(("131584_par_uniform_m50", 64, 2, 131584, 50, "prog-adaptive", 1))
+    LARGE_GOLDEN.append(("131584_par_nearest_group_m50", 64, 2, 131584, 50, "prog-adaptive", 3))
 
 
 @pytest.mark.parametrize("gold_name,radix,conns,n,msgs,routing,traffic", LARGE_GOLDEN, ids=[g[0] for g in LARGE_GOLDEN])
